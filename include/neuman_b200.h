@@ -1,0 +1,188 @@
+/*
+ * neuman_b200.h -- C ABI of the B200-native NeuMan ray-marching path.
+ *
+ * The reference (apple/ml-neuman) is one Python process with no plugin/FFI layer;
+ * the drop-in boundary is the set of Python functions listed below.  This header declares the
+ * C entry points that a binding of each of those functions calls -- `extern "C"`, plain pointers
+ * and sizes, no torch types.  Each entry cites the reference function it replaces (file:line in
+ * apple/ml-neuman).  INTEGRATION.md shows the ctypes binding (what neuman_b200/_lib.py does).
+ *
+ * Conventions
+ *   - return 0 on success, a negative nm_status otherwise; nm_last_error() gives the text.
+ *     Nothing throws across the boundary.
+ *   - all `const float*` / `float*` tensor arguments are DEVICE pointers to contiguous memory owned
+ *     by the caller (a torch CUDA tensor's data_ptr()), except in the *_host entry points and the
+ *     small camera / option structs, which are host memory.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; 0 = default stream)
+ *     unless stated otherwise.  A ctx is bound to one device and is not thread-safe.
+ *   - row-major everywhere; rays are [R,3], samples [R,S], raw network outputs [R,S,4]=(r,g,b,sigma).
+ */
+#ifndef NEUMAN_B200_H
+#define NEUMAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nm_ctx nm_ctx;
+
+typedef enum {
+  NM_OK = 0,
+  NM_ERR_INVALID = -1,     /* bad argument                              */
+  NM_ERR_CUDA = -2,        /* CUDA runtime error (see nm_last_error)    */
+  NM_ERR_UNSUPPORTED = -3, /* shape / option outside what is built      */
+  NM_ERR_STATE = -4        /* slot not packed, mesh not set, ...        */
+} nm_status;
+
+/* positional encoding kinds: models/vanilla.py:60-79 ('posenc'), :44-58 ('rotate') */
+enum { NM_PE_POSENC = 0, NM_PE_ROTATE = 1 };
+/* MLP arithmetic: tensor cores (fp16 operands, fp32 accumulate -- same 11-bit significand as TF32)
+ * or CUDA-core fp32 FMA (strict mode, used as the on-device cross-check). */
+enum { NM_MLP_TC_F16 = 0, NM_MLP_SIMT_F32 = 1 };
+
+#define NM_MAX_NET_SLOTS 16
+#define NM_MAX_ACTORS 8
+
+/* ---- context ------------------------------------------------------------------------------ */
+int nm_ctx_create(int device, nm_ctx** out);
+int nm_ctx_destroy(nm_ctx* ctx);
+const char* nm_last_error(const nm_ctx* ctx);
+/* library build id + the SM architecture the kernels were compiled for ("sm_100a") */
+const char* nm_version(void);
+/* number of kernels this library launched on ctx since creation (bench.py's gpu_launches) */
+int64_t nm_launch_count(const nm_ctx* ctx);
+
+/* ---- networks: models/vanilla.py:95-166 (NeRF, Joiner), build_nerf :208 ------------------- */
+typedef struct {
+  /* fp32 DEVICE pointers, nn.Linear layout [out,in] row-major, exactly the reference state dict:
+   * pts_linears.0 [256,63]; .1-.4,.6,.7 [256,256]; .5 [256,319] (input first, models/vanilla.py:131);
+   * feature_linear [256,256]; alpha_linear [1,256]; views_linears.0 [128,283] (feature first, :137);
+   * rgb_linear [3,128]. */
+  const float* pts_w[8];
+  const float* pts_b[8];
+  const float* feature_w; const float* feature_b;
+  const float* alpha_w;   const float* alpha_b;
+  const float* views_w;   const float* views_b;
+  const float* rgb_w;     const float* rgb_b;
+  int32_t pos_pe_kind;    /* NM_PE_* for the position input */
+  int32_t dir_pe_kind;    /* NM_PE_* for the view-direction input */
+  float pos_min_freq, pos_max_freq; int32_t pos_n_freqs;   /* options/options.py:62-66 */
+  float dir_min_freq, dir_max_freq; int32_t dir_n_freqs;   /* options/options.py:67-69 */
+} nm_nerf_desc;
+
+/* Re-pack the weights of one Joiner into the kernel layouts (fp16 UMMA tiles + fp32 transposed).
+ * Replaces nothing in the reference; it is the cost of `net.cuda()` / checkpoint load. */
+int nm_net_pack(nm_ctx* ctx, int slot, const nm_nerf_desc* desc, void* stream);
+
+/* Joiner.forward(input_pts, input_views) (models/vanilla.py:162-166) = Embedder.forward (:82-92)
+ * on both inputs + NeRF.forward (:120-152).  pts, views: [n,3]; raw: [n,4].
+ * If views_per_ray != 0, `views` is [n/views_per_ray, 3] and row i serves samples
+ * [i*views_per_ray, (i+1)*views_per_ray) (the renderers pass `dirs` stacked along samples). */
+int nm_mlp_forward(nm_ctx* ctx, int slot, int mode, const float* pts, const float* views,
+                   int64_t n, int32_t views_per_ray, float* raw, void* stream);
+
+/* Same network, but the sample positions are generated in-kernel: pts[r,s] = o[r] + d[r]*z[r,s],
+ * views = d[r] (utils/ray_utils.py:131-132).  o,d: [R,3]; z: [R,S]; raw: [R,S,4]. */
+int nm_mlp_forward_rays(nm_ctx* ctx, int slot, int mode, const float* origins, const float* dirs,
+                        const float* z, int64_t R, int32_t S, float* raw, void* stream);
+
+/* ---- rays: utils/ray_utils.py:23-38 (shot_rays, shot_all_rays) ---------------------------- */
+typedef struct {
+  double K[9];      /* intrinsic 3x3, row-major (cap.intrinsic_matrix)          */
+  double c2w[16];   /* camera_to_world 4x4 (cap.cam_pose.camera_to_world)        */
+  int32_t H, W;
+} nm_camera;
+
+/* mode 0: shot_rays semantics (point cast to f32, subtract + normalise in f32; :23-29)
+ * mode 1: shot_all_rays semantics (all f64, cast last; :32-38 + render_utils.py:114-115)
+ * Pixels are the row-major range [pix0, pix0+n) of the HxW grid, or, if xy != NULL, the n integer
+ * (x,y) pairs in xy (device int32 [n,2]). */
+int nm_raygen(nm_ctx* ctx, const nm_camera* cam, int mode, int64_t pix0, int64_t n,
+              const int32_t* xy, float* origins, float* dirs, void* stream);
+
+/* geometry_guided_near_far (utils/ray_utils.py:197-233): near/far [R]; miss => near=+inf,far=-inf */
+int nm_near_far(nm_ctx* ctx, const float* origins, const float* dirs, int64_t R,
+                const float* verts, int32_t n_verts, float geo_threshold,
+                float* near_out, float* far_out, void* stream);
+
+/* ray_to_samples (utils/ray_utils.py:96-135). near/far: [R] or NULL with the scalar fallback;
+ * t_rand: [R,S] uniforms for perturb>0 (clipped to [0.01,0.99] inside, :121-125) or NULL.
+ * pts/dirs may be NULL when only z is wanted. */
+int nm_ray_to_samples(nm_ctx* ctx, const float* origins, const float* dirs, const float* near_v,
+                      const float* far_v, float near_s, float far_s, int64_t R, int32_t S,
+                      int32_t lindisp, const float* t_rand, float* pts, float* dirs_out, float* z,
+                      void* stream);
+
+/* sample_pdf (utils/ray_utils.py:164-194): bins [R,B], weights [R,B-1], u: [R,N] or NULL (det=True
+ * linspace).  out [R,N]. */
+int nm_sample_pdf(nm_ctx* ctx, const float* bins, const float* weights, int64_t R, int32_t B,
+                  int32_t N, const float* u, float* out, void* stream);
+
+/* ray_to_importance_samples (utils/ray_utils.py:138-160), det=True: z [R,S], weights [R,S] ->
+ * z_out [R, S+N] sorted (including_old) or [R,N]; pts/dirs_out optional. */
+int nm_importance_samples(nm_ctx* ctx, const float* origins, const float* dirs, const float* z,
+                          const float* weights, int64_t R, int32_t S, int32_t N,
+                          int32_t including_old, float* pts, float* dirs_out, float* z_out,
+                          void* stream);
+
+/* raw2outputs (utils/render_utils.py:69-105).  noise: [R,S] added to sigma or NULL; sigma_scale
+ * folds `out[..., -1] *= interval_comp` (:229).  Any output pointer may be NULL. */
+int nm_raw2outputs(nm_ctx* ctx, const float* raw, const float* z, const float* rays_d, int64_t R,
+                   int32_t S, const float* noise, float sigma_scale, int32_t white_bkg,
+                   float* rgb, float* disp, float* acc, float* weights, float* depth, void* stream);
+
+/* z-sorted merge of several per-ray sample lists + gather of raw (utils/render_utils.py:330-337,
+ * :441-448): lists k=0..n_lists-1 with z_k [R,S_k], raw_k [R,S_k,4] -> z_out [R,sum S_k],
+ * raw_out [R,sum S_k,4].  Ties keep list order then sample order (stable). */
+int nm_merge_samples(nm_ctx* ctx, int32_t n_lists, const float* const* z_lists,
+                     const float* const* raw_lists, const int32_t* S_list, int64_t R,
+                     float* z_out, float* raw_out, void* stream);
+
+/* ---- observation -> canonical warp: utils/ray_utils.py:48-66 ------------------------------ */
+/* Per-frame mesh of one actor: verts [V,3] f32, faces [F,3] int32, T [>=V,4,4] f64 (HOST or DEVICE
+ * pointers, flag `on_device`).  Builds the closest-point acceleration grid. */
+int nm_mesh_set(nm_ctx* ctx, int actor, const float* verts, int32_t n_verts, const int32_t* faces,
+                int32_t n_faces, const double* T, int32_t n_T, int32_t on_device, void* stream);
+/* pts [R,S,3] f32 -> can_pts, can_dirs [R,S,3] f32 (the reference's float64 results cast with
+ * .float(), utils/render_utils.py:226-227); closest [R,S,3] f32 and face_id [R,S] optional. */
+int nm_warp_to_canonical(nm_ctx* ctx, int actor, const float* pts, int64_t R, int32_t S,
+                         float* can_pts, float* can_dirs, float* closest, int32_t* face_id,
+                         void* stream);
+
+/* ---- frame drivers: utils/render_utils.py:108-461 ----------------------------------------- */
+typedef struct {
+  int32_t samples_per_ray;              /* S */
+  int32_t importance_samples_per_ray;   /* N (0 = no fine pass) */
+  int32_t white_bkg;
+  int32_t mlp_mode;                     /* NM_MLP_* */
+  int32_t rays_per_batch;               /* device-side chunk; results do not depend on it */
+  int32_t render_can;                   /* render_smpl_nerf: skip the warp (:214-216) */
+  float near_bkg, far_bkg;              /* cap.near['bkg'], cap.far['bkg'] */
+  float geo_threshold;
+  float interval_comp;
+} nm_render_opts;
+
+/* All drivers render the row-major pixel range [pix0, pix0+n) (ray sharding across GPUs) into
+ * caller buffers rgb [n,3], depth [n], acc [n] (acc may be NULL).  `host_out` != 0: the output
+ * pointers are HOST memory and the call copies device->host and synchronises before returning. */
+int nm_render_vanilla(nm_ctx* ctx, int coarse_slot, int fine_slot /* -1 = none */,
+                      const nm_camera* cam, const nm_render_opts* opt, int64_t pix0, int64_t n,
+                      float* rgb, float* depth, int32_t host_out, void* stream);
+int nm_render_smpl_nerf(nm_ctx* ctx, int human_slot, int actor, const nm_camera* cam,
+                        const nm_render_opts* opt, int64_t pix0, int64_t n, float* rgb,
+                        float* depth, float* acc, int32_t host_out, void* stream);
+int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int32_t n_actors,
+                     const int32_t* human_slots, const int32_t* actors, int32_t multi_person,
+                     const nm_camera* cam, const nm_render_opts* opt, int64_t pix0, int64_t n,
+                     float* rgb, float* depth, float* acc, int32_t host_out, void* stream);
+
+/* statistics of the last driver call on this ctx: number of MLP evaluations executed (for the
+ * roofline: x 1,186,816 FLOP) and number of hit rays. */
+int nm_last_render_stats(const nm_ctx* ctx, int64_t* mlp_evals, int64_t* hit_rays);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUMAN_B200_H */

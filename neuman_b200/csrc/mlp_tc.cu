@@ -1,0 +1,621 @@
+// Tensor-core implementation of Joiner.forward (positional encoding + 8x256 NeRF MLP,
+// models/vanilla.py:82-92,:120-152,:162-166) for sm_100a: tcgen05.mma (kind::f16, fp16 operands,
+// fp32 accumulation in TMEM), weights streamed by bulk-TMA (cp.async.bulk) through a shared-memory
+// ring, activations kept on chip between layers, warp-specialised roles, persistent CTAs.
+//
+// fp16 operands carry the same 11-bit significand as TF32, at twice the tensor rate; accumulation,
+// bias, ReLU, the alpha head and the encodings are fp32 (DESIGN.md "Numerics").
+//
+// Work decomposition
+//   tile      = 128 consecutive samples per CTA (one TMEM lane per sample).  With kPair == 2 two
+//               CTAs of a cluster form a cta_group::2 pair: one 256-sample pair-tile, each CTA owns
+//               128 rows of A / D and HALF of every weight slab (N/2 rows of B).
+//   step      = one GEMM of the network: 0: L0 (K=64 PE) | 1-4: L1-4 | 5: L5 (PE block + 4 act
+//               blocks, "input first", :131) | 6,7: L6,L7 (+alpha head in the epilogue of 7, :135) |
+//               8: feature (:136) | 9: views layer (4 feature blocks + dir-PE block, N=128, :137-141) |
+//               10: rgb (N=16, 3 used, :143).
+//   slab      = one 64-wide K block of one step's weights for this CTA: [N_cta rows][128 B],
+//               128B-swizzled, K-major -- exactly the UMMA canonical layout, pre-packed in HBM so one
+//               cp.async.bulk moves it.  Slabs flow through an NSLOT-deep ring; with two tiles in
+//               flight a slab is consumed by tile A then tile B before its slot is released.
+//   warps     : 0 = bulk-TMA producer, 1 = TMEM allocator + MMA issuer (leader CTA) / relay (peer),
+//               2.. = epilogue warpgroups (one per tile in flight; thread == sample row).
+//   epilogue  : tcgen05.ld 32 columns -> +bias -> ReLU -> cvt to f16x2 -> swizzled st.shared into the
+//               tile's activation buffer, which is the next step's A operand (in place).
+//   on-chip   : act[NT][4 kblocks][128][128B] + one PE block shared by the tiles (the encodings live
+//               in the epilogue threads' registers and are written to it just before steps 0/5/9).
+#include "nm_internal.cuh"
+#include "nm_pe.cuh"
+
+#define TC_STEPS 11
+#define TC_KB_BYTES 16384          // one A k-block: 128 rows x 128 B
+#define TC_BIAS_STRIDE 256
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster (works for rank == self)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+template <int kPair>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  if (kPair == 2)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+template <int kPair>
+__device__ __forceinline__ void tmem_relinquish() {
+  if (kPair == 2) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  else asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kPair>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  if (kPair == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], fp16 operands, fp32 accumulate
+template <int kPair>
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  if (kPair == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+  }
+}
+// arrive::one on `bar` (same offset in every CTA of the pair) once all prior MMAs of this thread retire
+template <int kPair>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if (kPair == 2) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3) : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  }
+}
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=2 [61,64))
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// UMMA instruction descriptor, kind::f16: D=f32 (bit4), A=B=f16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// {lo, hi} -> packed f16x2 (lo in the low half), optional ReLU
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi, bool relu) {
+  uint32_t d;
+  if (relu) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Plan: which slabs a step consumes, where they live in the packed image.
+// ---------------------------------------------------------------------------------------------
+struct TcPlan {
+  uint32_t slab_off[TC_STEPS][5];   // byte offset inside one CTA-rank image
+  uint32_t slab_bytes[TC_STEPS];    // bytes per slab of this step (per CTA)
+  uint32_t image_bytes;             // size of one CTA-rank image
+};
+
+__host__ __device__ constexpr int step_nkb(int s) { return s == 0 ? 1 : (s == 5 || s == 9) ? 5 : (s == 10 ? 2 : 4); }
+__host__ __device__ constexpr int step_N(int s) { return s <= 8 ? 256 : (s == 9 ? 128 : 16); }
+// k-block kb of step s reads the PE buffer (else activation block `act_kb`)
+__host__ __device__ constexpr bool kb_is_pe(int s, int kb) { return (s == 0) || (s == 5 && kb == 0) || (s == 9 && kb == 4); }
+__host__ __device__ constexpr int kb_act_index(int s, int kb) { return s == 5 ? kb - 1 : kb; }
+__host__ __device__ constexpr int kb_ksteps(int s, int kb) { return (s == 9 && kb == 4) ? 2 : 4; }   // dir PE: K=32
+
+template <int kPair>
+struct TcCfg {
+  static constexpr int NT = kPair == 2 ? 2 : 1;
+  static constexpr int NSLOT = kPair == 2 ? 5 : 4;
+  static constexpr int SLOT_BYTES = 32768 / kPair;
+  static constexpr int THREADS = 64 + 128 * NT;
+  static constexpr int OFF_ACT = 0;
+  static constexpr int OFF_PE = OFF_ACT + NT * 4 * TC_KB_BYTES;
+  static constexpr int OFF_RING = OFF_PE + TC_KB_BYTES;
+  static constexpr int OFF_BAR = OFF_RING + NSLOT * SLOT_BYTES;
+  // barriers: full[NSLOT] peer_full[NSLOT] empty[NSLOT] tmem_full[NT] act_ready[NT] pe_free
+  static constexpr int N_BAR = 3 * NSLOT + 2 * NT + 1;
+  static constexpr int OFF_TMEMPTR = OFF_BAR + 8 * N_BAR;
+  static constexpr int SMEM_BYTES = OFF_TMEMPTR + 16 + 1024;   // + alignment slack
+};
+
+struct TcParams {
+  const uint8_t* wimg;      // packed slabs, kPair images back to back
+  const float* bias;        // [13][256]: steps 0-9, rgb bias, alpha weights, alpha bias
+  TcPlan plan;
+  NmMlpInput in;
+  NmPeSpec pos_pe, dir_pe;
+  float* raw;
+  long long n_tiles;        // number of (pair-)tiles
+};
+
+__device__ __noinline__ void nm_sincos(float a, float* s, float* c) { sincosf(a, s, c); }
+
+// Encodes x (3) into 64 f16 channels packed as 32 x f16x2; unused channels are zero.
+__device__ __forceinline__ void encode_f16(const NmPeSpec& pe, const float x[3], uint32_t (&out)[32], int nq) {
+  float ch[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) ch[i] = 0.f;
+  ch[0] = x[0]; ch[1] = x[1]; ch[2] = x[2];
+  if (pe.kind == NM_PE_ROTATE) {
+#pragma unroll
+    for (int q = 0; q < 30; ++q) {
+      if (q < nq) {
+        const float* b = pe.table + 3 * q;
+        float arg = fmaf(x[2], __ldg(b + 2), fmaf(x[1], __ldg(b + 1), x[0] * __ldg(b)));
+        float s, c;
+        nm_sincos(arg, &s, &c);
+        if (nq == 30) { ch[3 + q] = s; ch[33 + q] = c; }
+        else { ch[3 + q] = s; ch[15 + q] = c; }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      if (3 * k < nq) {
+        float f = __ldg(pe.table + k);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          float s, c;
+          nm_sincos(x[d] * f, &s, &c);
+          ch[3 + 6 * k + d] = s; ch[6 + 6 * k + d] = c;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) out[i] = pack_f16x2(ch[2 * i], ch[2 * i + 1], false);
+}
+
+// write 64 f16 (one 128-byte row of a K block) with the 128B swizzle
+__device__ __forceinline__ void store_row_swizzled(uint8_t* blk, int row, const uint32_t* v, int nchunks) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < nchunks) {
+      uint4 q = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      *reinterpret_cast<uint4*>(blk + row * 128 + ((j ^ (row & 7)) << 4)) = q;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------------------------
+template <int kPair>
+__global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcParams P) {
+  using C = TcCfg<kPair>;
+  constexpr int NT = C::NT, NSLOT = C::NSLOT;
+  extern __shared__ uint8_t smem_dyn[];
+  // 1024-byte alignment (SWIZZLE_128B atoms); identical offset in both CTAs of a pair
+  const uint32_t raw_addr = smem_u32(smem_dyn);
+  uint8_t* smem = smem_dyn + ((1024 - (raw_addr & 1023)) & 1023);
+  const uint32_t sbase = smem_u32(smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = kPair == 2 ? cluster_ctarank() : 0;
+  const long long pair_id = blockIdx.x / kPair;
+  const long long n_pairs = gridDim.x / kPair;
+
+  auto bar_full = [&](int i) { return sbase + C::OFF_BAR + 8 * i; };
+  auto bar_peer = [&](int i) { return sbase + C::OFF_BAR + 8 * (NSLOT + i); };
+  auto bar_empty = [&](int i) { return sbase + C::OFF_BAR + 8 * (2 * NSLOT + i); };
+  auto bar_tfull = [&](int t) { return sbase + C::OFF_BAR + 8 * (3 * NSLOT + t); };
+  auto bar_aready = [&](int t) { return sbase + C::OFF_BAR + 8 * (3 * NSLOT + NT + t); };
+  const uint32_t bar_pefree = sbase + C::OFF_BAR + 8 * (3 * NSLOT + 2 * NT);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEMPTR);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_peer(i), 1); mbar_init(bar_empty(i), 1); }
+    for (int t = 0; t < NT; ++t) { mbar_init(bar_tfull(t), 1); mbar_init(bar_aready(t), 4 * kPair); }
+    mbar_init(bar_pefree, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<kPair>(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish<kPair>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (kPair == 2) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const long long tiles_per_round = n_pairs * NT;
+  const long long n_rounds = (P.n_tiles + tiles_per_round - 1) / tiles_per_round;
+
+  if (warp == 0) {
+    // =============================== bulk-TMA producer ===============================
+    if (lane == 0) {
+      const uint8_t* img = P.wimg + (size_t)rank * P.plan.image_bytes;
+      uint32_t q = 0;
+      for (long long round = 0; round < n_rounds; ++round) {
+        for (int s = 0; s < TC_STEPS; ++s) {
+          const uint32_t bytes = P.plan.slab_bytes[s];
+          for (int kb = 0; kb < step_nkb(s); ++kb, ++q) {
+            const uint32_t slot = q % NSLOT, gen = q / NSLOT;
+            mbar_wait(bar_empty(slot), (gen & 1) ^ 1);
+            mbar_arrive_expect_tx(bar_full(slot), bytes);
+            bulk_g2s(sbase + C::OFF_RING + slot * C::SLOT_BYTES, img + P.plan.slab_off[s][kb], bytes, bar_full(slot));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // =============================== MMA issuer (leader CTA) ===============================
+      if (lane == 0) {
+        uint32_t q0 = 0, nstep = 0;
+        for (long long round = 0; round < n_rounds; ++round) {
+          for (int s = 0; s < TC_STEPS; ++s, ++nstep) {
+            const uint32_t idesc = make_idesc(128 * kPair, step_N(s));
+            const int nkb = step_nkb(s);
+            for (int t = 0; t < NT; ++t) {
+              mbar_wait(bar_aready(t), nstep & 1);          // A operand written, accumulator drained
+              tc_fence_after();
+              const uint32_t d_tmem = tmem_base + t * 256 + (s == 10 ? 128 : 0);
+              for (int kb = 0; kb < nkb; ++kb) {
+                const uint32_t q = q0 + kb, slot = q % NSLOT, gen = q / NSLOT;
+                if (t == 0) {
+                  mbar_wait(bar_full(slot), gen & 1);
+                  if (kPair == 2) mbar_wait(bar_peer(slot), gen & 1);
+                  tc_fence_after();
+                }
+                const bool is_pe = kb_is_pe(s, kb);
+                const uint32_t a_addr = is_pe ? sbase + C::OFF_PE
+                                              : sbase + C::OFF_ACT + (t * 4 + kb_act_index(s, kb)) * TC_KB_BYTES;
+                const uint32_t b_addr = sbase + C::OFF_RING + slot * C::SLOT_BYTES;
+                const int nk = kb_ksteps(s, kb);
+                for (int j = 0; j < nk; ++j)
+                  umma_f16<kPair>(d_tmem, make_desc(a_addr + 32 * j), make_desc(b_addr + 32 * j), idesc, (kb | j) != 0);
+                if (t == NT - 1) umma_commit<kPair>(bar_empty(slot));      // slab consumed by every tile
+                if (is_pe) umma_commit<kPair>(bar_pefree);                 // PE block may be rewritten
+              }
+              umma_commit<kPair>(bar_tfull(t));                            // accumulator complete
+            }
+            q0 += nkb;
+          }
+        }
+      }
+    } else {
+      // =============================== relay (peer CTA of a pair) ===============================
+      // tells the leader's MMA thread that this CTA's half of a slab has landed
+      if (lane == 0) {
+        uint32_t q = 0;
+        for (long long round = 0; round < n_rounds; ++round)
+          for (int s = 0; s < TC_STEPS; ++s)
+            for (int kb = 0; kb < step_nkb(s); ++kb, ++q) {
+              const uint32_t slot = q % NSLOT, gen = q / NSLOT;
+              mbar_wait(bar_full(slot), gen & 1);
+              mbar_arrive_cluster(bar_peer(slot), 0);
+            }
+      }
+    }
+  } else {
+    // =============================== epilogue warpgroups ===============================
+    const int t = (warp - 2) >> 2;                 // tile slot served by this warpgroup
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;              // sample row inside the CTA tile
+    uint8_t* act = smem + C::OFF_ACT + t * 4 * TC_KB_BYTES;
+    uint8_t* pebuf = smem + C::OFF_PE;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + t * 256;
+    const float* bias = P.bias;
+    uint32_t nstep = 0;
+
+    auto publish = [&]() {                          // A operand ready + accumulator drained
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(bar_aready(t), 0);
+    };
+    // PE-buffer use index u (order of the MMA stream: per round A0,B0,A5,B5,A9,B9); the writer of use u
+    // waits until the MMAs of use u-1 have retired
+    auto wait_pe_slot = [&](long long round, int k) {
+      long long u = (round * 3 + k) * NT + t;
+      if (u > 0) mbar_wait(bar_pefree, (uint32_t)((u - 1) & 1));
+    };
+
+    for (long long round = 0; round < n_rounds; ++round) {
+      const long long tile = (round * n_pairs + pair_id) * NT + t;
+      const long long i = (tile * kPair + rank) * 128 + row;          // global sample index
+      const bool valid = tile < P.n_tiles && i < P.in.n;
+      uint32_t pe_pos[32], pe_dir[16];
+      {
+        float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
+        if (valid) nm_fetch_sample(P.in, i, p, v);
+        encode_f16(P.pos_pe, p, pe_pos, 30);
+        uint32_t tmp[32];
+        encode_f16(P.dir_pe, v, tmp, 12);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pe_dir[j] = tmp[j];
+      }
+      // ---- step 0 input: positional encoding block ----
+      wait_pe_slot(round, 0);
+      store_row_swizzled(pebuf, row, pe_pos, 8);
+      publish();
+      float alpha = 0.f;
+      for (int s = 0; s < TC_STEPS; ++s, ++nstep) {
+        mbar_wait(bar_tfull(t), nstep & 1);
+        tc_fence_after();
+        if (s < 10) {
+          const int ncols = step_N(s);                    // 256 or 128
+          const bool relu = (s != 8);
+          const float* b = bias + s * TC_BIAS_STRIDE;
+#pragma unroll 1
+          for (int c0 = 0; c0 < ncols; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(t_lane + c0, v);
+            tmem_wait_ld();
+            uint32_t packed[16];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c0) + g);
+              float x0 = __uint_as_float(v[4 * g + 0]) + bb.x, x1 = __uint_as_float(v[4 * g + 1]) + bb.y;
+              float x2 = __uint_as_float(v[4 * g + 2]) + bb.z, x3 = __uint_as_float(v[4 * g + 3]) + bb.w;
+              if (s == 7) {                               // alpha_linear on the fp32 ReLU output (:135)
+                const float4 aw = __ldg(reinterpret_cast<const float4*>(bias + 11 * TC_BIAS_STRIDE + c0) + g);
+                alpha = fmaf(fmaxf(x0, 0.f), aw.x, alpha); alpha = fmaf(fmaxf(x1, 0.f), aw.y, alpha);
+                alpha = fmaf(fmaxf(x2, 0.f), aw.z, alpha); alpha = fmaf(fmaxf(x3, 0.f), aw.w, alpha);
+              }
+              packed[2 * g] = pack_f16x2(x0, x1, relu);
+              packed[2 * g + 1] = pack_f16x2(x2, x3, relu);
+            }
+            // 32 columns = 4 chunks of 16 B in k-block c0/64
+            uint8_t* blk = act + (c0 >> 6) * TC_KB_BYTES + row * 128;
+            const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(blk + (((ch0 + j) ^ (row & 7)) << 4)) =
+                  make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          }
+          if (s == 4) { wait_pe_slot(round, 1); store_row_swizzled(pebuf, row, pe_pos, 8); }    // skip input (:131)
+          if (s == 8) { wait_pe_slot(round, 2); store_row_swizzled(pebuf, row, pe_dir, 4); }    // view dirs (:137)
+          publish();
+        } else {
+          uint32_t v[4];
+          tmem_ld4(t_lane + 128, v);
+          tmem_wait_ld();
+          if (valid) {
+            const float* rb = bias + 10 * TC_BIAS_STRIDE;
+            float4 o = make_float4(__uint_as_float(v[0]) + __ldg(rb), __uint_as_float(v[1]) + __ldg(rb + 1),
+                                   __uint_as_float(v[2]) + __ldg(rb + 2), alpha + __ldg(bias + 12 * TC_BIAS_STRIDE));
+            reinterpret_cast<float4*>(P.raw)[i] = o;                       // [r,g,b,sigma] (:144)
+          }
+          tc_fence_before();
+        }
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (kPair == 2) cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kPair>(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packing: fp32 nn.Linear weights -> fp16 slabs in the swizzled UMMA layout.
+// ---------------------------------------------------------------------------------------------
+struct PackSrc {
+  const float* w[8]; const float* feat; const float* views; const float* rgb;
+};
+
+// weight of (step s, output n, k-block kb, kk in [0,64)) or 0 for padding
+__device__ __forceinline__ float src_weight(const PackSrc& S, int s, int n, int kb, int kk) {
+  if (s == 0) return kk < NM_POS_PE ? S.w[0][(size_t)n * NM_POS_PE + kk] : 0.f;
+  if (s >= 1 && s <= 7 && s != 5) return S.w[s][(size_t)n * 256 + kb * 64 + kk];
+  if (s == 5) {
+    const int ld = NM_POS_PE + 256;
+    if (kb == 0) return kk < NM_POS_PE ? S.w[5][(size_t)n * ld + kk] : 0.f;
+    return S.w[5][(size_t)n * ld + NM_POS_PE + (kb - 1) * 64 + kk];
+  }
+  if (s == 8) return S.feat[(size_t)n * 256 + kb * 64 + kk];
+  if (s == 9) {
+    const int ld = 256 + NM_DIR_PE;
+    if (kb < 4) return S.views[(size_t)n * ld + kb * 64 + kk];
+    return kk < NM_DIR_PE ? S.views[(size_t)n * ld + 256 + kk] : 0.f;
+  }
+  // s == 10: rgb, N padded 3 -> 16
+  return n < 3 ? S.rgb[(size_t)n * 128 + kb * 64 + kk] : 0.f;
+}
+
+__global__ void k_tc_pack(PackSrc S, TcPlan plan, int kpair, __half* __restrict__ out) {
+  // one thread per packed element of one CTA-rank image; grid.y = rank
+  const int rank = blockIdx.y;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // half index inside the image
+  if (e * 2 >= plan.image_bytes) return;
+  const uint32_t byte = (uint32_t)(e * 2);
+  // locate (s, kb)
+  int s = 0, kb = 0;
+  for (int ss = 0; ss < TC_STEPS; ++ss)
+    for (int k = 0; k < step_nkb(ss); ++k)
+      if (byte >= plan.slab_off[ss][k]) { s = ss; kb = k; }
+  const uint32_t in_slab = byte - plan.slab_off[s][kb];
+  const int n_local = in_slab >> 7;
+  const int chunk_phys = (in_slab & 127) >> 4;
+  const int chunk = chunk_phys ^ (n_local & 7);                         // undo the 128B swizzle
+  const int kk = chunk * 8 + ((in_slab & 15) >> 1);
+  const int n_cta = step_N(s) / kpair;
+  const int n = rank * n_cta + n_local;
+  out[(size_t)rank * (plan.image_bytes / 2) + e] = __float2half_rn(src_weight(S, s, n, kb, kk));
+}
+
+__global__ void k_tc_bias(const float* b0, const float* b1, const float* b2, const float* b3, const float* b4,
+                          const float* b5, const float* b6, const float* b7, const float* feat_b, const float* views_b,
+                          const float* rgb_b, const float* alpha_w, const float* alpha_b, float* __restrict__ out) {
+  const int i = threadIdx.x;      // 256 threads
+  const float* bs[8] = {b0, b1, b2, b3, b4, b5, b6, b7};
+  for (int s = 0; s < 8; ++s) out[s * TC_BIAS_STRIDE + i] = bs[s][i];
+  out[8 * TC_BIAS_STRIDE + i] = feat_b[i];
+  out[9 * TC_BIAS_STRIDE + i] = i < 128 ? views_b[i] : 0.f;
+  out[10 * TC_BIAS_STRIDE + i] = i < 3 ? rgb_b[i] : 0.f;
+  out[11 * TC_BIAS_STRIDE + i] = alpha_w[i];
+  out[12 * TC_BIAS_STRIDE + i] = i == 0 ? alpha_b[0] : 0.f;
+}
+
+static int tc_pair_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("NEUMAN_TC_PAIR");
+    mode = (e && e[0] == '1') ? 1 : 2;
+  }
+  return mode;
+}
+
+static TcPlan make_plan(int kpair) {
+  TcPlan p{};
+  uint32_t off = 0;
+  for (int s = 0; s < TC_STEPS; ++s) {
+    p.slab_bytes[s] = (uint32_t)(step_N(s) / kpair) * 128u;
+    for (int kb = 0; kb < step_nkb(s); ++kb) { p.slab_off[s][kb] = off; off += p.slab_bytes[s]; }
+  }
+  p.image_bytes = off;
+  return p;
+}
+
+bool nm_tc_available() { return true; }
+
+int nm_tc_pack(nm_ctx* ctx, NmNet& net, cudaStream_t st) {
+  const int kpair = tc_pair_mode();
+  TcPlan plan = make_plan(kpair);
+  const size_t halfs = (size_t)kpair * plan.image_bytes / 2;
+  if (!net.f16 || net.f16_halfs != halfs) {
+    if (net.f16) { NM_CHECK_CUDA(ctx, cudaDeviceSynchronize()); NM_CHECK_CUDA(ctx, cudaFree(net.f16)); net.f16 = nullptr; }
+    NM_CHECK_CUDA(ctx, cudaMalloc(&net.f16, halfs * sizeof(__half)));
+    net.f16_halfs = halfs;
+  }
+  if (!net.tc_bias) NM_CHECK_CUDA(ctx, cudaMalloc(&net.tc_bias, 13 * TC_BIAS_STRIDE * sizeof(float)));
+  const nm_nerf_desc& d = net.desc;
+  PackSrc S;
+  for (int l = 0; l < 8; ++l) S.w[l] = d.pts_w[l];
+  S.feat = d.feature_w; S.views = d.views_w; S.rgb = d.rgb_w;
+  dim3 grid((unsigned)((plan.image_bytes / 2 + 255) / 256), kpair);
+  k_tc_pack<<<grid, 256, 0, st>>>(S, plan, kpair, net.f16);
+  NM_CHECK_LAUNCH(ctx);
+  k_tc_bias<<<1, 256, 0, st>>>(d.pts_b[0], d.pts_b[1], d.pts_b[2], d.pts_b[3], d.pts_b[4], d.pts_b[5], d.pts_b[6],
+                               d.pts_b[7], d.feature_b, d.views_b, d.rgb_b, d.alpha_w, d.alpha_b, net.tc_bias);
+  NM_CHECK_LAUNCH(ctx);
+  return NM_OK;
+}
+
+template <int kPair>
+static int launch_tc(nm_ctx* ctx, const TcParams& P, cudaStream_t st) {
+  using C = TcCfg<kPair>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NM_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_mlp_tc<kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  int ctas = ctx->sm_count - (ctx->sm_count % kPair);
+  long long need = P.n_tiles * kPair;                       // CTAs that have work in the first round
+  need = (need + C::NT - 1) / C::NT;
+  if (need < ctas) ctas = (int)((need + kPair - 1) / kPair * kPair);
+  if (ctas < kPair) ctas = kPair;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NM_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_mlp_tc<kPair>, P));
+  NM_LAUNCHED(ctx);
+  return NM_OK;
+}
+
+int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* views, const float* origins,
+                  const float* dirs, const float* z, int64_t n, int32_t group, float* raw, cudaStream_t st) {
+  const int kpair = tc_pair_mode();
+  if (!net.f16 || !net.tc_bias) NM_FAIL(ctx, NM_ERR_STATE, "nm_tc_forward: weights not packed");
+  TcParams P;
+  P.wimg = reinterpret_cast<const uint8_t*>(net.f16);
+  P.bias = net.tc_bias;
+  P.plan = make_plan(kpair);
+  P.in = NmMlpInput{pts, views, origins, dirs, z, (long long)n, group};
+  P.pos_pe = NmPeSpec{net.desc.pos_pe_kind, net.desc.pos_n_freqs, net.f32 + net.o_pos_bv};
+  P.dir_pe = NmPeSpec{net.desc.dir_pe_kind, net.desc.dir_n_freqs, net.f32 + net.o_dir_bv};
+  P.raw = raw;
+  P.n_tiles = (n + 128 * kpair - 1) / (128 * kpair);
+  return kpair == 2 ? launch_tc<2>(ctx, P, st) : launch_tc<1>(ctx, P, st);
+}

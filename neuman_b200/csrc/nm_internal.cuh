@@ -1,0 +1,117 @@
+// Internal declarations shared by the translation units of libneuman_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "neuman_b200.h"
+
+#define NM_WIDTH 256          // nerf_width  (options/options.py:55)
+#define NM_DEPTH 8            // nerf_depth  (options/options.py:54)
+#define NM_POS_PE 63          // 3 + 3*2*10  (models/vanilla.py:60-79)
+#define NM_DIR_PE 27          // 3 + 3*2*4
+#define NM_VIEWS_HID 128      // width/2     (models/vanilla.py:112)
+
+// ---- packed network ------------------------------------------------------------------------
+// fp32 transposed weights ([in_padded][out]) for the SIMT kernel and fp16 UMMA-tiled weights for
+// the tensor-core kernel live in one device allocation per slot.
+struct NmNet {
+  bool packed = false;
+  nm_nerf_desc desc{};
+  // SIMT fp32 layout: Wt[k][n] (k = input index, n = output index), biases as given
+  float* f32 = nullptr;             // base allocation
+  size_t f32_floats = 0;
+  // offsets (in floats) into f32
+  size_t o_pts_w[8], o_pts_b[8], o_feat_w, o_feat_b, o_alpha_w, o_alpha_b, o_views_w, o_views_b,
+      o_rgb_w, o_rgb_b, o_pos_bv, o_dir_bv;
+  // tensor-core layout (see mlp_tc.cu for the tile format)
+  __half* f16 = nullptr;
+  size_t f16_halfs = 0;
+  float* tc_bias = nullptr;         // concatenated fp32 biases + alpha weights for the epilogues
+};
+
+struct NmMesh {
+  bool set = false;
+  int32_t n_verts = 0, n_faces = 0, n_T = 0;
+  float* verts = nullptr;      // [V,3] f32
+  int32_t* faces = nullptr;    // [F,3]
+  double* T = nullptr;         // [n_T,16] f64
+  // acceleration grid (warp.cu)
+  float4* tri_sphere = nullptr;   // [F] centroid xyz + radius
+  int32_t* cell_start = nullptr;  // [ncell+1]
+  int32_t* cell_tris = nullptr;   // [n_refs]
+  int32_t n_refs = 0;
+  float3 grid_min = {0, 0, 0};
+  float cell = 0.f;
+  int3 dims = {0, 0, 0};
+  size_t cap_refs = 0, cap_cells = 0, cap_verts = 0, cap_faces = 0, cap_T = 0;
+};
+
+struct nm_ctx {
+  int device = 0;
+  int sm_count = 148;
+  std::string err;
+  int64_t launches = 0;
+  NmNet nets[NM_MAX_NET_SLOTS];
+  NmMesh meshes[NM_MAX_ACTORS];
+  // grow-only workspace arena for the frame drivers
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  int64_t last_mlp_evals = 0;
+  int64_t last_hit_rays = 0;
+  int32_t* d_counter = nullptr;   // small device scratch (compaction counters)
+  int32_t* h_counter = nullptr;   // pinned host mirror
+  double* can64 = nullptr;        // float64 canonical points scratch (warp.cu)
+  size_t can64_cap = 0;
+};
+
+#define NM_CHECK_CUDA(ctx, call)                                                         \
+  do {                                                                                   \
+    cudaError_t _e = (call);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                   ":" + std::to_string(__LINE__) + ")";                                 \
+      return NM_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define NM_FAIL(ctx, code, msg)     \
+  do {                              \
+    (ctx)->err = (msg);             \
+    return (code);                  \
+  } while (0)
+
+#define NM_LAUNCHED(ctx) ((ctx)->launches++)
+
+#define NM_CHECK_LAUNCH(ctx)                 \
+  do {                                       \
+    NM_LAUNCHED(ctx);                        \
+    NM_CHECK_CUDA(ctx, cudaGetLastError());  \
+  } while (0)
+
+// torch.linspace(0, 1, steps) element i in float32: ATen computes start + i*step for the first half
+// and end - (steps-1-i)*step for the second half, step = (end-start)/(steps-1).
+// Compile units that use this are built with -fmad=false so nothing is contracted.
+__host__ __device__ __forceinline__ float nm_linspace01(int i, int steps) {
+  if (steps <= 1) return 0.f;
+  const float step = 1.0f / (float)(steps - 1);
+  if (i < steps / 2) return (float)i * step;
+  return 1.0f - (float)(steps - 1 - i) * step;
+}
+
+// ---- implemented in the individual .cu files ------------------------------------------------
+int nm_impl_workspace(nm_ctx* ctx, size_t bytes, char** out);
+
+// mlp_simt.cu
+int nm_simt_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* views,
+                    const float* origins, const float* dirs, const float* z, int64_t n,
+                    int32_t group, float* raw, cudaStream_t st);
+// mlp_tc.cu
+int nm_tc_pack(nm_ctx* ctx, NmNet& net, cudaStream_t st);
+int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* views,
+                  const float* origins, const float* dirs, const float* z, int64_t n,
+                  int32_t group, float* raw, cudaStream_t st);
+bool nm_tc_available();

@@ -1,0 +1,196 @@
+// Ray generation, SMPL-guided near/far, and per-ray sample placement.
+// Compiled with -fmad=false: these kernels mirror chains of separately-rounded torch/numpy
+// elementwise ops, so nothing may be contracted into FMAs.
+//
+//   nm_raygen           <- utils/ray_utils.py:23-38 + geometry/pcd_projector.py:85-120
+//   nm_near_far         <- utils/ray_utils.py:197-233
+//   nm_ray_to_samples   <- utils/ray_utils.py:96-135
+#include "nm_internal.cuh"
+
+// ---------------------------------------------------------------------------------------------
+struct RaygenParams {
+  double Kinv[9];
+  double c2w[16];
+  int W;
+  int mode;
+  long long pix0, n;
+};
+
+__global__ void __launch_bounds__(256) k_raygen(RaygenParams p, const int32_t* __restrict__ xy,
+                                                 float* __restrict__ origins, float* __restrict__ dirs) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  double x, y;
+  if (xy) {
+    x = (double)xy[2 * i];
+    y = (double)xy[2 * i + 1];
+  } else {
+    long long pix = p.pix0 + i;
+    y = (double)(pix / p.W);      // row-major, y outer (render_utils.py:185)
+    x = (double)(pix % p.W);
+  }
+  // camera-space point at depth 1: Kinv * [x, y, 1]
+  double cx = p.Kinv[0] * x + p.Kinv[1] * y + p.Kinv[2];
+  double cy = p.Kinv[3] * x + p.Kinv[4] * y + p.Kinv[5];
+  double cz = p.Kinv[6] * x + p.Kinv[7] * y + p.Kinv[8];
+  // world = c2w * [c;1], then / w
+  double wx = p.c2w[0] * cx + p.c2w[1] * cy + p.c2w[2] * cz + p.c2w[3];
+  double wy = p.c2w[4] * cx + p.c2w[5] * cy + p.c2w[6] * cz + p.c2w[7];
+  double wz = p.c2w[8] * cx + p.c2w[9] * cy + p.c2w[10] * cz + p.c2w[11];
+  double ww = p.c2w[12] * cx + p.c2w[13] * cy + p.c2w[14] * cz + p.c2w[15];
+  wx /= ww; wy /= ww; wz /= ww;
+  float ox = (float)p.c2w[3], oy = (float)p.c2w[7], oz = (float)p.c2w[11];
+  float dx, dy, dz;
+  if (p.mode == 0) {
+    // shot_rays: point cast to f32, subtraction and normalisation in f32 (ray_utils.py:25-28)
+    float fx = (float)wx - ox, fy = (float)wy - oy, fz = (float)wz - oz;
+    float nrm = sqrtf(fx * fx + fy * fy + fz * fz);
+    dx = fx / nrm; dy = fy / nrm; dz = fz / nrm;
+  } else {
+    // shot_all_rays: float64 throughout, cast last (ray_utils.py:34-37, render_utils.py:114-115)
+    double ex = wx - (double)ox, ey = wy - (double)oy, ez = wz - (double)oz;
+    double nrm = sqrt(ex * ex + ey * ey + ez * ez);
+    dx = (float)(ex / nrm); dy = (float)(ey / nrm); dz = (float)(ez / nrm);
+  }
+  origins[3 * i + 0] = ox; origins[3 * i + 1] = oy; origins[3 * i + 2] = oz;
+  dirs[3 * i + 0] = dx; dirs[3 * i + 1] = dy; dirs[3 * i + 2] = dz;
+}
+
+static void invert3x3(const double* m, double* o) {
+  double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+  double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+  double id = 1.0 / det;
+  o[0] = (e * i - f * h) * id; o[1] = (c * h - b * i) * id; o[2] = (b * f - c * e) * id;
+  o[3] = (f * g - d * i) * id; o[4] = (a * i - c * g) * id; o[5] = (c * d - a * f) * id;
+  o[6] = (d * h - e * g) * id; o[7] = (b * g - a * h) * id; o[8] = (a * e - b * d) * id;
+}
+
+extern "C" int nm_raygen(nm_ctx* ctx, const nm_camera* cam, int mode, int64_t pix0, int64_t n,
+                         const int32_t* xy, float* origins, float* dirs, void* stream) {
+  if (!ctx) return NM_ERR_INVALID;
+  if (!cam || !origins || !dirs || n < 0 || (mode != 0 && mode != 1))
+    NM_FAIL(ctx, NM_ERR_INVALID, "nm_raygen: bad argument");
+  if (n == 0) return NM_OK;
+  RaygenParams p;
+  invert3x3(cam->K, p.Kinv);
+  for (int i = 0; i < 16; ++i) p.c2w[i] = cam->c2w[i];
+  p.W = cam->W; p.mode = mode; p.pix0 = pix0; p.n = n;
+  if (!xy && (pix0 < 0 || pix0 + n > (int64_t)cam->H * cam->W))
+    NM_FAIL(ctx, NM_ERR_INVALID, "nm_raygen: pixel range outside the image");
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  k_raygen<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, xy, origins, dirs);
+  NM_CHECK_LAUNCH(ctx);
+  return NM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// near/far: one thread per ray, the vertex list streamed through shared memory in tiles.
+// 6890 vertices x 16 B = 110 KB: two tiles of 4096.
+#define NF_TILE 2048
+__global__ void __launch_bounds__(128) k_near_far(const float* __restrict__ origins,
+                                                   const float* __restrict__ dirs, long long R,
+                                                   const float* __restrict__ verts, int nv, float thr2,
+                                                   float* __restrict__ near_out, float* __restrict__ far_out) {
+  __shared__ float4 sv[NF_TILE];
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = r < R;
+  float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1;
+  if (live) {
+    ox = origins[3 * r]; oy = origins[3 * r + 1]; oz = origins[3 * r + 2];
+    dx = dirs[3 * r]; dy = dirs[3 * r + 1]; dz = dirs[3 * r + 2];
+  }
+  float nr = INFINITY, fr = -INFINITY;
+  for (int base = 0; base < nv; base += NF_TILE) {
+    int cnt = min(NF_TILE, nv - base);
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+      const float* v = verts + 3 * (size_t)(base + j);
+      sv[j] = make_float4(v[0], v[1], v[2], 0.f);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      float4 v = sv[j];
+      float ax = v.x - ox, ay = v.y - oy, az = v.z - oz;          // orig_v (ray_utils.py:211)
+      float z0 = ax * dx + ay * dy + az * dz;                      // einsum (:212)
+      float nrm = sqrtf(ax * ax + ay * ay + az * az);              // torch.norm (:213)
+      float disc = thr2 - (nrm * nrm - z0 * z0);
+      if (disc >= 0.f) {                                           // sqrt of a negative -> NaN -> skipped
+        float dzv = sqrtf(disc);
+        nr = fminf(nr, z0 - dzv);
+        fr = fmaxf(fr, z0 + dzv);
+      }
+    }
+  }
+  if (live) { near_out[r] = nr; far_out[r] = fr; }
+}
+
+extern "C" int nm_near_far(nm_ctx* ctx, const float* origins, const float* dirs, int64_t R,
+                           const float* verts, int32_t n_verts, float geo_threshold, float* near_out,
+                           float* far_out, void* stream) {
+  if (!ctx) return NM_ERR_INVALID;
+  if (!origins || !dirs || !verts || !near_out || !far_out || R < 0 || n_verts < 0)
+    NM_FAIL(ctx, NM_ERR_INVALID, "nm_near_far: bad argument");
+  if (R == 0) return NM_OK;
+  // geo_threshold**2 is a python double that torch casts to f32 for the subtraction (:213)
+  float thr2 = (float)((double)geo_threshold * (double)geo_threshold);
+  unsigned blocks = (unsigned)((R + 127) / 128);
+  k_near_far<<<blocks, 128, 0, (cudaStream_t)stream>>>(origins, dirs, R, verts, n_verts, thr2, near_out, far_out);
+  NM_CHECK_LAUNCH(ctx);
+  return NM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ray_to_samples: thread per sample (coalesced along the sample index).
+__global__ void __launch_bounds__(256) k_ray_to_samples(
+    const float* __restrict__ origins, const float* __restrict__ dirs, const float* __restrict__ near_v,
+    const float* __restrict__ far_v, float near_s, float far_s, long long R, int S, int lindisp,
+    const float* __restrict__ t_rand, float* __restrict__ pts, float* __restrict__ dirs_out,
+    float* __restrict__ z_out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * (long long)S) return;
+  long long r = idx / S;
+  int s = (int)(idx - r * S);
+  float nr = near_v ? near_v[r] : near_s;
+  float fr = far_v ? far_v[r] : far_s;
+  auto zval = [&](int i) -> float {
+    float t = nm_linspace01(i, S);
+    if (!lindisp) return nr * (1.f - t) + fr * t;                       // (:113)
+    return 1.f / (1.f / nr * (1.f - t) + 1.f / fr * t);                 // (:115)
+  };
+  float z = zval(s);
+  if (t_rand) {                                                          // stratified (:117-129)
+    float zl = s > 0 ? zval(s - 1) : z;
+    float zu = s < S - 1 ? zval(s + 1) : z;
+    float lower = s > 0 ? 0.5f * (z + zl) : z;
+    float upper = s < S - 1 ? 0.5f * (zu + z) : z;
+    float u = fminf(fmaxf(t_rand[idx], 0.01f), 1.f - 0.01f);            // PERTURB_EPSILON
+    z = lower + (upper - lower) * u;
+  }
+  if (z_out) z_out[idx] = z;
+  if (pts || dirs_out) {
+    float dx = dirs[3 * r], dy = dirs[3 * r + 1], dz = dirs[3 * r + 2];
+    if (pts) {
+      pts[3 * idx + 0] = origins[3 * r + 0] + dx * z;                   // (:131)
+      pts[3 * idx + 1] = origins[3 * r + 1] + dy * z;
+      pts[3 * idx + 2] = origins[3 * r + 2] + dz * z;
+    }
+    if (dirs_out) { dirs_out[3 * idx] = dx; dirs_out[3 * idx + 1] = dy; dirs_out[3 * idx + 2] = dz; }
+  }
+}
+
+extern "C" int nm_ray_to_samples(nm_ctx* ctx, const float* origins, const float* dirs, const float* near_v,
+                                 const float* far_v, float near_s, float far_s, int64_t R, int32_t S,
+                                 int32_t lindisp, const float* t_rand, float* pts, float* dirs_out, float* z,
+                                 void* stream) {
+  if (!ctx) return NM_ERR_INVALID;
+  if (R < 0 || S <= 0 || ((pts || dirs_out) && (!origins || !dirs)))
+    NM_FAIL(ctx, NM_ERR_INVALID, "nm_ray_to_samples: bad argument");
+  if (R == 0) return NM_OK;
+  long long total = (long long)R * S;
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  k_ray_to_samples<<<blocks, 256, 0, (cudaStream_t)stream>>>(origins, dirs, near_v, far_v, near_s, far_s, R, S,
+                                                               lindisp, t_rand, pts, dirs_out, z);
+  NM_CHECK_LAUNCH(ctx);
+  return NM_OK;
+}

@@ -1,0 +1,79 @@
+"""Drop-in: rebinds the reference's hot-path functions to the CUDA path.
+
+    import neuman_b200; neuman_b200.install("/path/to/ml-neuman")
+    # or: python -m neuman_b200.run render_test_views.py --scene_dir ...
+
+After install(), `utils.render_utils.render_vanilla / render_smpl_nerf / render_hybrid_nerf /
+render_hybrid_nerf_multi_persons / raw2outputs`, `utils.ray_utils.ray_to_samples /
+ray_to_importance_samples / sample_pdf` and `models.vanilla.Joiner.forward` (inference, CUDA tensors,
+grad disabled) run on libneuman_b200; the reference's nn.Modules, checkpoints and CLI scripts are
+untouched.  Calls that need autograd (training) keep the reference's own torch implementation.
+"""
+import importlib
+import sys
+
+import torch
+
+
+def install(reference_root=None):
+    if reference_root and reference_root not in sys.path:
+        sys.path.insert(0, reference_root)
+    from . import ops, render
+    ru = importlib.import_module("utils.render_utils")
+    ry = importlib.import_module("utils.ray_utils")
+    mv = importlib.import_module("models.vanilla")
+
+    def on_cuda_nograd(*ts):
+        return (not torch.is_grad_enabled()) and all(isinstance(t, torch.Tensor) and t.is_cuda for t in ts)
+
+    ref_forward = mv.Joiner.forward
+
+    def joiner_forward(self, input_pts, input_views=None):
+        if input_views is not None and on_cuda_nograd(input_pts, input_views) and self.nerf.use_viewdirs:
+            return ops.joiner_forward(self, input_pts, input_views)
+        return ref_forward(self, input_pts, input_views)          # training / CPU: reference torch path
+    mv.Joiner.forward = joiner_forward
+
+    ref_raw2outputs = ru.raw2outputs
+
+    def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkg=True):
+        if on_cuda_nograd(raw, z_vals, rays_d):
+            return ops.raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkg)
+        return ref_raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkg)
+    ru.raw2outputs = raw2outputs
+
+    def cuda_model(m):
+        return next(m.parameters()).is_cuda
+
+    for name in ("render_vanilla", "render_smpl_nerf", "render_hybrid_nerf", "render_hybrid_nerf_multi_persons"):
+        ref_fn, new_fn = getattr(ru, name), getattr(render, name)
+
+        def make(ref_fn=ref_fn, new_fn=new_fn):
+            def wrapped(model, *a, **k):
+                if cuda_model(model):
+                    return new_fn(model, *a, **k)
+                return ref_fn(model, *a, **k)
+            wrapped.__name__ = ref_fn.__name__
+            return wrapped
+        setattr(ru, name, make())
+
+    ref_rts, ref_rtis, ref_pdf = ry.ray_to_samples, ry.ray_to_importance_samples, ry.sample_pdf
+
+    def ray_to_samples(ray_batch, samples_per_ray, lindisp=False, perturb=0., device='cpu', append_t=None):
+        if append_t is None and on_cuda_nograd(ray_batch['origin'], ray_batch['near']):
+            return ops.ray_to_samples(ray_batch, samples_per_ray, lindisp, perturb)
+        return ref_rts(ray_batch, samples_per_ray, lindisp, perturb, device, append_t)
+
+    def ray_to_importance_samples(ray_batch, z_vals, weights, importance_samples_per_ray, device='cpu',
+                                  including_old=True, append_t=None):
+        if append_t is None and on_cuda_nograd(z_vals, weights):
+            return ops.ray_to_importance_samples(ray_batch, z_vals, weights, importance_samples_per_ray,
+                                                 including_old=including_old)
+        return ref_rtis(ray_batch, z_vals, weights, importance_samples_per_ray, device, including_old, append_t)
+
+    def sample_pdf(bins, weights, N_samples, det=False, device='cpu'):
+        if on_cuda_nograd(bins, weights):
+            return ops.sample_pdf(bins, weights, N_samples, det)
+        return ref_pdf(bins, weights, N_samples, det, device)
+    ry.ray_to_samples, ry.ray_to_importance_samples, ry.sample_pdf = ray_to_samples, ray_to_importance_samples, sample_pdf
+    return {"render_utils": ru, "ray_utils": ry, "vanilla": mv}

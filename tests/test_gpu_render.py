@@ -1,0 +1,104 @@
+"""GPU parity of the frame drivers against the reference goldens (small frames) and the oracle, plus
+size-independent properties at BASELINE.json's full frame sizes."""
+import numpy as np
+import pytest
+import torch
+
+import neuman_b200 as nb
+from neuman_b200 import render
+from oracle import neuman_oracle as no
+from oracle import scenes
+from tests import util
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-4         # north_star: rendered RGB / depth <= 1e-4 abs vs the reference path (fp32)
+
+
+@pytest.fixture(scope="module")
+def nets():
+    return tuple(n.to(DEV) for n in util.product_nets())
+
+
+@pytest.fixture(scope="module")
+def human():
+    return util.product_human_model(DEV)
+
+
+def test_cfg1_vanilla_64x64(nets):
+    """BASELINE configs[0]: vanilla background NeRF, 64x64, 64 coarse samples."""
+    f = util.golden("frames.npz")
+    cap = nb.SimpleCapture(f["cfg1_K"], f["cfg1_c2w"], 64, 64, 0.0, 3.14)
+    rgb, dep = nb.render_vanilla(nets[0], cap, fine_net=None, samples_per_ray=64, return_depth=True)
+    assert rgb.dtype == np.float32 and rgb.shape == (64, 64, 3) and dep.shape == (64, 64)
+    assert np.abs(rgb - f["cfg1_rgb"]).max() < TOL and np.abs(dep - f["cfg1_depth"]).max() < TOL
+    assert round(util.psnr(rgb, f["cfg1_rgb"]), 2) >= 70.0
+
+
+def test_vanilla_coarse_fine_ragged(nets):
+    f = util.golden("frames.npz")
+    cap = nb.SimpleCapture(f["van_K"], f["van_c2w"], 20, 28, 0.0, 3.14)
+    rgb, dep = nb.render_vanilla(nets[0], cap, fine_net=nets[1], samples_per_ray=48, importance_samples_per_ray=40,
+                                 return_depth=True)
+    assert np.abs(rgb - f["van_rgb"]).max() < TOL and np.abs(dep - f["van_depth"]).max() < 3 * TOL
+    rgb = nb.render_vanilla(nets[0], cap, fine_net=nets[1], samples_per_ray=48, importance_samples_per_ray=40, white_bkg=False)
+    assert np.abs(rgb - f["van_rgb_black"]).max() < TOL
+
+
+def test_human_renderers_golden(human):
+    f = util.golden("frames.npz")
+    b1, b2 = util.bodies()
+    H, W = f["hyb_rgb"].shape[:2]
+    cap = nb.SimpleCapture(f["h_K"], f["h_c2w"], H, W, 0.0, 3.14)
+    geo = b1["geo_threshold"]
+
+    def close(a, ref, tol, what):
+        err = np.abs(a - ref)
+        # grazing rays (hit/miss decided by an ill-conditioned sqrt) may flip: allow <1% outlier pixels
+        bad = (err > tol).reshape(H * W, -1).any(-1).mean()
+        assert bad < 0.01, (what, bad, err.max())
+
+    for can in (1, 0):
+        r, d, a = nb.render_smpl_nerf(human, cap, b1["verts"], b1["faces"], b1["Ts"], samples_per_ray=24,
+                                      render_can=bool(can), geo_threshold=geo, return_depth=True, return_mask=True,
+                                      interval_comp=0.7)
+        close(r, f[f"smpl{can}_rgb"], TOL, f"smpl{can} rgb")
+        close(d, f[f"smpl{can}_depth"], TOL, f"smpl{can} depth")
+        close(a, f[f"smpl{can}_acc"], TOL, f"smpl{can} acc")
+    r, d = nb.render_hybrid_nerf(human, cap, b1["verts"], b1["faces"], b1["Ts"], samples_per_ray=24,
+                                 importance_samples_per_ray=16, geo_threshold=geo, return_depth=True)
+    close(r, f["hyb_rgb"], TOL, "hybrid rgb")
+    close(d, f["hyb_depth"], 3 * TOL, "hybrid depth")
+    r, d = nb.render_hybrid_nerf_multi_persons(human, cap, [human, human], [b1["verts"], b2["verts"]],
+                                               [b1["faces"]] * 2, [b1["Ts"], b2["Ts"]], samples_per_ray=24,
+                                               importance_samples_per_ray=16, geo_threshold=geo, return_depth=True)
+    close(r, f["multi_rgb"], TOL, "multi rgb")
+    close(d, f["multi_depth"], 3 * TOL, "multi depth")
+
+
+def test_full_size_properties(nets):
+    """1280x720, 128+128 (the benchmark workload): results do not depend on the device chunking or on
+    how the frame is sharded into pixel ranges; white-vs-black background differ by exactly 1-acc; a
+    4096-ray subsample agrees with the oracle."""
+    H, W = 720, 1280
+    K, c2w = scenes.camera(H, W, seed=1)
+    cap = nb.SimpleCapture(K, c2w, H, W, 0.0, 3.14)
+    n = H * W
+    sub0, cnt = 300 * W + 17, 6000
+    a_rgb, a_dep = render.render_vanilla_range(nets[0], cap, nets[1], 128, 128, pix0=sub0, n=cnt, host_out=False)
+    b_rgb, b_dep = render.render_vanilla_range(nets[0], cap, nets[1], 128, 128, pix0=sub0, n=cnt, host_out=False, chunk=1000)
+    assert torch.equal(a_rgb, b_rgb) and torch.equal(a_dep, b_dep)               # chunk-invariant
+    c_rgb, _ = render.render_vanilla_range(nets[0], cap, nets[1], 128, 128, pix0=sub0 + 1000, n=2000, host_out=False)
+    assert torch.equal(c_rgb, a_rgb[1000:3000])                                  # shard-invariant
+    k_rgb, _ = render.render_vanilla_range(nets[0], cap, nets[1], 128, 128, white_bkg=False, pix0=sub0, n=cnt, host_out=False)
+    assert ((a_rgb - k_rgb) >= -1e-6).all() and ((a_rgb - k_rgb) <= 1 + 1e-6).all()
+    # oracle on the first 1024 rays of the range
+    idx = np.arange(sub0, sub0 + 1024)
+    cp, fp = (util.oracle_params(m.to("cpu")) for m in nets[:2])
+    for m in nets:
+        m.to(DEV)
+    rgb_o, dep_o = no.render_vanilla(cp, fp, K, c2w, H, W, 0.0, 3.14, samples_per_ray=128, importance_samples_per_ray=128,
+                                     ray_subset=idx)
+    rgb = a_rgb[:1024].cpu().numpy()
+    assert np.abs(rgb - rgb_o).max() < TOL and np.abs(a_dep[:1024].cpu().numpy() - dep_o).max() < 3 * TOL
+    assert abs(round(util.psnr(rgb, 0.5 * np.ones_like(rgb)), 2) - round(util.psnr(rgb_o, 0.5 * np.ones_like(rgb)), 2)) <= 0.01
