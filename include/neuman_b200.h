@@ -178,6 +178,12 @@ int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int32_t n_acto
                      const nm_camera* cam, const nm_render_opts* opt, int64_t pix0, int64_t n,
                      float* rgb, float* depth, float* acc, int32_t host_out, void* stream);
 
+/* Optional timing of the MLP kernel launches (the dominant kernel; bench.py's roofline): when enabled,
+ * every MLP launch is bracketed by CUDA events on its own stream.  nm_profile_read synchronises on
+ * them and returns the summed device time, the number of launches and of network evaluations. */
+int nm_profile_enable(nm_ctx* ctx, int32_t on);
+int nm_profile_read(nm_ctx* ctx, double* mlp_ms, int64_t* mlp_launches, int64_t* mlp_evals);
+
 /* statistics of the last driver call on this ctx: number of MLP evaluations executed (for the
  * roofline: x 1,186,816 FLOP) and number of hit rays. */
 int nm_last_render_stats(const nm_ctx* ctx, int64_t* mlp_evals, int64_t* hit_rays);

@@ -65,6 +65,8 @@ SIGNATURES = {
                                       _P, _P, _P, _I32, _P]),
     "nm_render_hybrid": (C.c_int, [_P, C.c_int, C.c_int, _I32, C.POINTER(_I32), C.POINTER(_I32), _I32,
                                    C.POINTER(NmCamera), C.POINTER(NmRenderOpts), _I64, _I64, _P, _P, _P, _I32, _P]),
+    "nm_profile_enable": (C.c_int, [_P, _I32]),
+    "nm_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(_I64), C.POINTER(_I64)]),
     "nm_last_render_stats": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),
 }
 
@@ -125,6 +127,14 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.nm_launch_count(self.h))
+
+    def profile(self, on):
+        self.check(self.lib.nm_profile_enable(self.h, int(bool(on))))
+
+    def profile_read(self):
+        ms, nl, ne = C.c_double(), _I64(), _I64()
+        self.check(self.lib.nm_profile_read(self.h, C.byref(ms), C.byref(nl), C.byref(ne)))
+        return {"mlp_ms": ms.value, "mlp_launches": nl.value, "mlp_evals": ne.value}
 
     def render_stats(self):
         a, b = _I64(), _I64()

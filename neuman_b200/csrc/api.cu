@@ -50,6 +50,7 @@ extern "C" int nm_ctx_destroy(nm_ctx* ctx) {
   for (auto& m : ctx->meshes) free_mesh(m);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->can64) cudaFree(ctx->can64);
+  for (auto e : ctx->prof_events) cudaEventDestroy(e);
   if (ctx->d_counter) cudaFree(ctx->d_counter);
   if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
   delete ctx;
@@ -58,6 +59,29 @@ extern "C" int nm_ctx_destroy(nm_ctx* ctx) {
 
 extern "C" const char* nm_last_error(const nm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 extern "C" int64_t nm_launch_count(const nm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int nm_profile_enable(nm_ctx* ctx, int32_t on) {
+  if (!ctx) return NM_ERR_INVALID;
+  ctx->profile = on != 0;
+  ctx->prof_used = 0;
+  ctx->prof_evals = 0;
+  return NM_OK;
+}
+
+extern "C" int nm_profile_read(nm_ctx* ctx, double* mlp_ms, int64_t* mlp_launches, int64_t* mlp_evals) {
+  if (!ctx) return NM_ERR_INVALID;
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+    NM_CHECK_CUDA(ctx, cudaEventSynchronize(ctx->prof_events[i + 1]));
+    float ms = 0.f;
+    NM_CHECK_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
+    total += ms;
+  }
+  if (mlp_ms) *mlp_ms = total;
+  if (mlp_launches) *mlp_launches = (int64_t)(ctx->prof_used / 2);
+  if (mlp_evals) *mlp_evals = ctx->prof_evals;
+  return NM_OK;
+}
 
 extern "C" int nm_last_render_stats(const nm_ctx* ctx, int64_t* mlp_evals, int64_t* hit_rays) {
   if (!ctx) return NM_ERR_INVALID;
@@ -192,9 +216,29 @@ static int mlp_dispatch(nm_ctx* ctx, int slot, int mode, const float* pts, const
   if (n < 0 || !raw) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward: bad argument");
   if (n == 0) return NM_OK;
   const NmNet& net = ctx->nets[slot];
-  if (mode == NM_MLP_SIMT_F32) return nm_simt_forward(ctx, net, pts, views, origins, dirs, z, n, group, raw, (cudaStream_t)stream);
-  if (mode == NM_MLP_TC_F16) return nm_tc_forward(ctx, net, pts, views, origins, dirs, z, n, group, raw, (cudaStream_t)stream);
-  NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward: unknown mode");
+  if (mode != NM_MLP_SIMT_F32 && mode != NM_MLP_TC_F16) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward: unknown mode");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->profile) {
+    if (ctx->prof_used + 2 > ctx->prof_events.size()) {
+      for (int k = 0; k < 2; ++k) {
+        cudaEvent_t e;
+        NM_CHECK_CUDA(ctx, cudaEventCreate(&e));
+        ctx->prof_events.push_back(e);
+      }
+    }
+    e0 = ctx->prof_events[ctx->prof_used];
+    e1 = ctx->prof_events[ctx->prof_used + 1];
+    NM_CHECK_CUDA(ctx, cudaEventRecord(e0, st));
+  }
+  int rc = mode == NM_MLP_SIMT_F32 ? nm_simt_forward(ctx, net, pts, views, origins, dirs, z, n, group, raw, st)
+                                   : nm_tc_forward(ctx, net, pts, views, origins, dirs, z, n, group, raw, st);
+  if (ctx->profile && rc == NM_OK) {
+    NM_CHECK_CUDA(ctx, cudaEventRecord(e1, st));
+    ctx->prof_used += 2;
+    ctx->prof_evals += n;
+  }
+  return rc;
 }
 
 extern "C" int nm_mlp_forward(nm_ctx* ctx, int slot, int mode, const float* pts, const float* views, int64_t n,

@@ -74,7 +74,10 @@ __global__ void __launch_bounds__(256) k_raw2outputs(
     if (rgb_out) { rgb_out[3 * r] = s_r; rgb_out[3 * r + 1] = s_g; rgb_out[3 * r + 2] = s_b; }
     if (depth_out) depth_out[r] = s_d;
     if (acc_out) acc_out[r] = s_a;
-    if (disp_out) disp_out[r] = 1.f / fmaxf(1e-10f, s_d / s_a);         // (:99)
+    if (disp_out) {                                                    // (:99) torch.max propagates NaN (0/0)
+      float q = s_d / s_a;
+      disp_out[r] = 1.f / ((q != q) ? q : fmaxf(1e-10f, q));
+    }
   }
 }
 

@@ -196,7 +196,8 @@ struct TcCfg {
 
 struct TcParams {
   const uint8_t* wimg;      // packed slabs, kPair images back to back
-  const float* bias;        // [13][256]: steps 0-9, rgb bias, alpha weights, alpha bias
+  const float* bias;        // [12][256] global copy of the bias table (see TcBias)
+  int cslot;                // index of the net's table in c_tc_bias, or -1
   TcPlan plan;
   NmMlpInput in;
   NmPeSpec pos_pe, dir_pe;
@@ -254,9 +255,58 @@ __device__ __forceinline__ void store_row_swizzled(uint8_t* blk, int row, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Biases (+ alpha weights): [12][256] floats per net = rows 0-9 the steps' biases, row 10 =
+// {rgb_b0, rgb_b1, rgb_b2, alpha_b}, row 11 = alpha_linear weights.  Up to TC_CONST_NETS nets keep
+// their table in __constant__ memory (every lane reads the same address: a constant-cache
+// broadcast, no shared memory needed -- the 227 KB are full); further nets read it from global.
+// ---------------------------------------------------------------------------------------------
+#define TC_BIAS_ROWS 12
+#define TC_BIAS_FLOATS (TC_BIAS_ROWS * TC_BIAS_STRIDE)
+#define TC_CONST_NETS 5
+__constant__ float c_tc_bias[TC_CONST_NETS * TC_BIAS_FLOATS];
+
+struct TcBias {
+  const float* g;     // global table
+  int coff;           // float offset of this net inside c_tc_bias
+  template <bool kConst>
+  __device__ __forceinline__ float4 ld(int idx4) const {
+    if (kConst) return reinterpret_cast<const float4*>(c_tc_bias + coff)[idx4];
+    return __ldg(reinterpret_cast<const float4*>(g) + idx4);
+  }
+};
+
+// one 32-column chunk of an epilogue: +bias, (alpha head), ReLU, f16x2 pack, swizzled store
+template <bool kConst>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const TcBias& bsrc, int s, int c0, bool relu,
+                                          float& alpha, uint8_t* act, int row) {
+  uint32_t packed[16];
+  const int b4 = (s * TC_BIAS_STRIDE + c0) >> 2;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 bb = bsrc.template ld<kConst>(b4 + g);
+    float x0 = __uint_as_float(v[4 * g + 0]) + bb.x, x1 = __uint_as_float(v[4 * g + 1]) + bb.y;
+    float x2 = __uint_as_float(v[4 * g + 2]) + bb.z, x3 = __uint_as_float(v[4 * g + 3]) + bb.w;
+    if (s == 7) {                               // alpha_linear on the fp32 ReLU output (:135)
+      const float4 aw = bsrc.template ld<kConst>(((11 * TC_BIAS_STRIDE + c0) >> 2) + g);
+      alpha = fmaf(fmaxf(x0, 0.f), aw.x, alpha); alpha = fmaf(fmaxf(x1, 0.f), aw.y, alpha);
+      alpha = fmaf(fmaxf(x2, 0.f), aw.z, alpha); alpha = fmaf(fmaxf(x3, 0.f), aw.w, alpha);
+    }
+    packed[2 * g] = pack_f16x2(x0, x1, relu);
+    packed[2 * g + 1] = pack_f16x2(x2, x3, relu);
+  }
+  // 32 columns = 4 chunks of 16 B in k-block c0/64
+  uint8_t* blk = act + (c0 >> 6) * TC_KB_BYTES + row * 128;
+  const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(blk + (((ch0 + j) ^ (row & 7)) << 4)) =
+        make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
-template <int kPair>
+template <int kPair, bool kConst>
 __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcParams P) {
   using C = TcCfg<kPair>;
   constexpr int NT = C::NT, NSLOT = C::NSLOT;
@@ -373,7 +423,7 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
     uint8_t* act = smem + C::OFF_ACT + t * 4 * TC_KB_BYTES;
     uint8_t* pebuf = smem + C::OFF_PE;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + t * 256;
-    const float* bias = P.bias;
+    const TcBias bsrc{P.bias, P.cslot * TC_BIAS_FLOATS};
     uint32_t nstep = 0;
 
     auto publish = [&]() {                          // A operand ready + accumulator drained
@@ -412,35 +462,19 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
         mbar_wait(bar_tfull(t), nstep & 1);
         tc_fence_after();
         if (s < 10) {
-          const int ncols = step_N(s);                    // 256 or 128
+          const int niter = step_N(s) >> 5;               // 8 or 4 chunks of 32 columns
           const bool relu = (s != 8);
-          const float* b = bias + s * TC_BIAS_STRIDE;
+          // software pipeline: the tcgen05.ld of chunk it+1 is in flight while chunk it is processed
+          uint32_t va[32], vb[32];
+          tmem_ld32(t_lane, va);
 #pragma unroll 1
-          for (int c0 = 0; c0 < ncols; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(t_lane + c0, v);
+          for (int it = 0; it < niter; it += 2) {
             tmem_wait_ld();
-            uint32_t packed[16];
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c0) + g);
-              float x0 = __uint_as_float(v[4 * g + 0]) + bb.x, x1 = __uint_as_float(v[4 * g + 1]) + bb.y;
-              float x2 = __uint_as_float(v[4 * g + 2]) + bb.z, x3 = __uint_as_float(v[4 * g + 3]) + bb.w;
-              if (s == 7) {                               // alpha_linear on the fp32 ReLU output (:135)
-                const float4 aw = __ldg(reinterpret_cast<const float4*>(bias + 11 * TC_BIAS_STRIDE + c0) + g);
-                alpha = fmaf(fmaxf(x0, 0.f), aw.x, alpha); alpha = fmaf(fmaxf(x1, 0.f), aw.y, alpha);
-                alpha = fmaf(fmaxf(x2, 0.f), aw.z, alpha); alpha = fmaf(fmaxf(x3, 0.f), aw.w, alpha);
-              }
-              packed[2 * g] = pack_f16x2(x0, x1, relu);
-              packed[2 * g + 1] = pack_f16x2(x2, x3, relu);
-            }
-            // 32 columns = 4 chunks of 16 B in k-block c0/64
-            uint8_t* blk = act + (c0 >> 6) * TC_KB_BYTES + row * 128;
-            const int ch0 = (c0 & 63) >> 3;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(blk + (((ch0 + j) ^ (row & 7)) << 4)) =
-                  make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            tmem_ld32(t_lane + (it + 1) * 32, vb);
+            epi_chunk<kConst>(va, bsrc, s, it * 32, relu, alpha, act, row);
+            tmem_wait_ld();
+            if (it + 2 < niter) tmem_ld32(t_lane + (it + 2) * 32, va);
+            epi_chunk<kConst>(vb, bsrc, s, (it + 1) * 32, relu, alpha, act, row);
           }
           if (s == 4) { wait_pe_slot(round, 1); store_row_swizzled(pebuf, row, pe_pos, 8); }    // skip input (:131)
           if (s == 8) { wait_pe_slot(round, 2); store_row_swizzled(pebuf, row, pe_dir, 4); }    // view dirs (:137)
@@ -450,9 +484,9 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
           tmem_ld4(t_lane + 128, v);
           tmem_wait_ld();
           if (valid) {
-            const float* rb = bias + 10 * TC_BIAS_STRIDE;
-            float4 o = make_float4(__uint_as_float(v[0]) + __ldg(rb), __uint_as_float(v[1]) + __ldg(rb + 1),
-                                   __uint_as_float(v[2]) + __ldg(rb + 2), alpha + __ldg(bias + 12 * TC_BIAS_STRIDE));
+            const float4 rb = bsrc.template ld<kConst>(10 * (TC_BIAS_STRIDE / 4));     // rgb bias (3) + alpha bias
+            float4 o = make_float4(__uint_as_float(v[0]) + rb.x, __uint_as_float(v[1]) + rb.y,
+                                   __uint_as_float(v[2]) + rb.z, alpha + rb.w);
             reinterpret_cast<float4*>(P.raw)[i] = o;                       // [r,g,b,sigma] (:144)
           }
           tc_fence_before();
@@ -526,9 +560,8 @@ __global__ void k_tc_bias(const float* b0, const float* b1, const float* b2, con
   for (int s = 0; s < 8; ++s) out[s * TC_BIAS_STRIDE + i] = bs[s][i];
   out[8 * TC_BIAS_STRIDE + i] = feat_b[i];
   out[9 * TC_BIAS_STRIDE + i] = i < 128 ? views_b[i] : 0.f;
-  out[10 * TC_BIAS_STRIDE + i] = i < 3 ? rgb_b[i] : 0.f;
+  out[10 * TC_BIAS_STRIDE + i] = i < 3 ? rgb_b[i] : (i == 3 ? alpha_b[0] : 0.f);
   out[11 * TC_BIAS_STRIDE + i] = alpha_w[i];
-  out[12 * TC_BIAS_STRIDE + i] = i == 0 ? alpha_b[0] : 0.f;
 }
 
 static int tc_pair_mode() {
@@ -562,7 +595,7 @@ int nm_tc_pack(nm_ctx* ctx, NmNet& net, cudaStream_t st) {
     NM_CHECK_CUDA(ctx, cudaMalloc(&net.f16, halfs * sizeof(__half)));
     net.f16_halfs = halfs;
   }
-  if (!net.tc_bias) NM_CHECK_CUDA(ctx, cudaMalloc(&net.tc_bias, 13 * TC_BIAS_STRIDE * sizeof(float)));
+  if (!net.tc_bias) NM_CHECK_CUDA(ctx, cudaMalloc(&net.tc_bias, TC_BIAS_FLOATS * sizeof(float)));
   const nm_nerf_desc& d = net.desc;
   PackSrc S;
   for (int l = 0; l < 8; ++l) S.w[l] = d.pts_w[l];
@@ -573,15 +606,19 @@ int nm_tc_pack(nm_ctx* ctx, NmNet& net, cudaStream_t st) {
   k_tc_bias<<<1, 256, 0, st>>>(d.pts_b[0], d.pts_b[1], d.pts_b[2], d.pts_b[3], d.pts_b[4], d.pts_b[5], d.pts_b[6],
                                d.pts_b[7], d.feature_b, d.views_b, d.rgb_b, d.alpha_w, d.alpha_b, net.tc_bias);
   NM_CHECK_LAUNCH(ctx);
+  const int slot = (int)(&net - ctx->nets);
+  if (slot >= 0 && slot < TC_CONST_NETS)
+    NM_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tc_bias, net.tc_bias, TC_BIAS_FLOATS * sizeof(float),
+                                               (size_t)slot * TC_BIAS_FLOATS * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return NM_OK;
 }
 
-template <int kPair>
+template <int kPair, bool kConst>
 static int launch_tc(nm_ctx* ctx, const TcParams& P, cudaStream_t st) {
   using C = TcCfg<kPair>;
   static bool attr_set = false;
   if (!attr_set) {
-    NM_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_mlp_tc<kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    NM_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_mlp_tc<kPair, kConst>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   int ctas = ctx->sm_count - (ctx->sm_count % kPair);
@@ -599,7 +636,7 @@ static int launch_tc(nm_ctx* ctx, const TcParams& P, cudaStream_t st) {
   attr[0].val.clusterDim.x = kPair; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NM_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_mlp_tc<kPair>, P));
+  NM_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_mlp_tc<kPair, kConst>, P));
   NM_LAUNCHED(ctx);
   return NM_OK;
 }
@@ -617,5 +654,8 @@ int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* 
   P.dir_pe = NmPeSpec{net.desc.dir_pe_kind, net.desc.dir_n_freqs, net.f32 + net.o_dir_bv};
   P.raw = raw;
   P.n_tiles = (n + 128 * kpair - 1) / (128 * kpair);
-  return kpair == 2 ? launch_tc<2>(ctx, P, st) : launch_tc<1>(ctx, P, st);
+  const int slot = (int)(&net - ctx->nets);
+  P.cslot = (slot >= 0 && slot < TC_CONST_NETS) ? slot : -1;
+  if (P.cslot >= 0) return kpair == 2 ? launch_tc<2, true>(ctx, P, st) : launch_tc<1, true>(ctx, P, st);
+  return kpair == 2 ? launch_tc<2, false>(ctx, P, st) : launch_tc<1, false>(ctx, P, st);
 }

@@ -65,6 +65,11 @@ struct nm_ctx {
   int32_t* d_counter = nullptr;   // small device scratch (compaction counters)
   int32_t* h_counter = nullptr;   // pinned host mirror
   double* can64 = nullptr;        // float64 canonical points scratch (warp.cu)
+  // optional per-launch timing of the MLP kernel (bench.py roofline): event pairs on the launch stream
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;   // start0, stop0, start1, stop1, ...
+  size_t prof_used = 0;
+  int64_t prof_evals = 0;
   size_t can64_cap = 0;
 };
 
