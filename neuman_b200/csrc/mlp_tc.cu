@@ -59,7 +59,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}" ::"r"(bar), "r"(rank) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
@@ -148,6 +148,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
@@ -191,13 +199,16 @@ struct TcCfg {
   // barriers: full[NSLOT] peer_full[NSLOT] empty[NSLOT] tmem_full[NT] act_ready[NT] pe_free
   static constexpr int N_BAR = 3 * NSLOT + 2 * NT + 1;
   static constexpr int OFF_TMEMPTR = OFF_BAR + 8 * N_BAR;
-  static constexpr int SMEM_BYTES = OFF_TMEMPTR + 16 + 1024;   // + alignment slack
+  // per-warpgroup copy of the current step's bias row (256 fp32), refreshed each step by the warpgroup
+  static constexpr int OFF_BIAS = (OFF_TMEMPTR + 16 + 127) & ~127;
+  static constexpr int SMEM_USED = OFF_BIAS + NT * 1024;
+  static constexpr int SMEM_SLACK = (232448 - SMEM_USED) < 1024 ? (232448 - SMEM_USED) : 1024;   // alignment slack that still fits 227 KB
+  static constexpr int SMEM_BYTES = SMEM_USED + SMEM_SLACK;
 };
 
 struct TcParams {
   const uint8_t* wimg;      // packed slabs, kPair images back to back
-  const float* bias;        // [12][256] global copy of the bias table (see TcBias)
-  int cslot;                // index of the net's table in c_tc_bias, or -1
+  const float* bias;        // [12][256]: rows 0-9 the steps' biases, row 10 = {rgb_b0,rgb_b1,rgb_b2,alpha_b}, row 11 = alpha weights
   TcPlan plan;
   NmMlpInput in;
   NmPeSpec pos_pe, dir_pe;
@@ -255,65 +266,92 @@ __device__ __forceinline__ void store_row_swizzled(uint8_t* blk, int row, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Biases (+ alpha weights): [12][256] floats per net = rows 0-9 the steps' biases, row 10 =
-// {rgb_b0, rgb_b1, rgb_b2, alpha_b}, row 11 = alpha_linear weights.  Up to TC_CONST_NETS nets keep
-// their table in __constant__ memory (every lane reads the same address: a constant-cache
-// broadcast, no shared memory needed -- the 227 KB are full); further nets read it from global.
+// Epilogue of one 32-column chunk: +bias (from the warpgroup's shared-memory copy of the step's bias
+// row: every lane reads the same address, a broadcast), the alpha head on step 7 (alpha weights are
+// spread over the lanes' registers, 8 per lane, and fetched by shuffle), ReLU, f16x2 pack, swizzled
+// 16-byte stores into the activation block that is the next step's A operand.
 // ---------------------------------------------------------------------------------------------
 #define TC_BIAS_ROWS 12
 #define TC_BIAS_FLOATS (TC_BIAS_ROWS * TC_BIAS_STRIDE)
-#define TC_CONST_NETS 5
-__constant__ float c_tc_bias[TC_CONST_NETS * TC_BIAS_FLOATS];
 
-struct TcBias {
-  const float* g;     // global table
-  int coff;           // float offset of this net inside c_tc_bias
-  template <bool kConst>
-  __device__ __forceinline__ float4 ld(int idx4) const {
-    if (kConst) return reinterpret_cast<const float4*>(c_tc_bias + coff)[idx4];
-    return __ldg(reinterpret_cast<const float4*>(g) + idx4);
-  }
-};
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t d;
+  if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 
-// one 32-column chunk of an epilogue: +bias, (alpha head), ReLU, f16x2 pack, swizzled store
-template <bool kConst>
-__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const TcBias& bsrc, int s, int c0, bool relu,
-                                          float& alpha, uint8_t* act, int row) {
-  uint32_t packed[16];
-  const int b4 = (s * TC_BIAS_STRIDE + c0) >> 2;
+__device__ __forceinline__ void load_bias16(float4 (&b)[4], const float* sbias) {
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    const float4 bb = bsrc.template ld<kConst>(b4 + g);
-    float x0 = __uint_as_float(v[4 * g + 0]) + bb.x, x1 = __uint_as_float(v[4 * g + 1]) + bb.y;
-    float x2 = __uint_as_float(v[4 * g + 2]) + bb.z, x3 = __uint_as_float(v[4 * g + 3]) + bb.w;
-    if (s == 7) {                               // alpha_linear on the fp32 ReLU output (:135)
-      const float4 aw = bsrc.template ld<kConst>(((11 * TC_BIAS_STRIDE + c0) >> 2) + g);
-      alpha = fmaf(fmaxf(x0, 0.f), aw.x, alpha); alpha = fmaf(fmaxf(x1, 0.f), aw.y, alpha);
-      alpha = fmaf(fmaxf(x2, 0.f), aw.z, alpha); alpha = fmaf(fmaxf(x3, 0.f), aw.w, alpha);
+  for (int g = 0; g < 4; ++g) b[g] = *reinterpret_cast<const float4*>(sbias + 4 * g);
+}
+
+// 16 accumulator columns [c0, c0+16) of one row: +bias, (alpha head), ReLU, pack, two swizzled 16-byte stores
+template <bool RELU, bool ALPHA>
+__device__ __forceinline__ void epi_sub16(const uint32_t (&v)[16], const float4 (&b)[4], const float (&aw)[8], int c0,
+                                          float& alpha, uint8_t* act, int row) {
+  uint32_t packed[8];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float x0 = __uint_as_float(v[4 * g + 0]) + b[g].x, x1 = __uint_as_float(v[4 * g + 1]) + b[g].y;
+    float x2 = __uint_as_float(v[4 * g + 2]) + b[g].z, x3 = __uint_as_float(v[4 * g + 3]) + b[g].w;
+    if (ALPHA) {                                // alpha_linear on the fp32 ReLU output (:135)
+      // column c = c0 + 4g + j lives in lane c/8, register c%8
+      const int src = (c0 >> 3) + (g >> 1), r0 = (g & 1) * 4;
+      alpha = fmaf(fmaxf(x0, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 0], src), alpha);
+      alpha = fmaf(fmaxf(x1, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 1], src), alpha);
+      alpha = fmaf(fmaxf(x2, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 2], src), alpha);
+      alpha = fmaf(fmaxf(x3, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 3], src), alpha);
     }
-    packed[2 * g] = pack_f16x2(x0, x1, relu);
-    packed[2 * g + 1] = pack_f16x2(x2, x3, relu);
+    packed[2 * g] = pack2<RELU>(x0, x1);
+    packed[2 * g + 1] = pack2<RELU>(x2, x3);
   }
-  // 32 columns = 4 chunks of 16 B in k-block c0/64
   uint8_t* blk = act + (c0 >> 6) * TC_KB_BYTES + row * 128;
   const int ch0 = (c0 & 63) >> 3;
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    *reinterpret_cast<uint4*>(blk + (((ch0 + j) ^ (row & 7)) << 4)) =
-        make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+  *reinterpret_cast<uint4*>(blk + ((ch0 ^ (row & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  *reinterpret_cast<uint4*>(blk + (((ch0 + 1) ^ (row & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+}
+
+// Drains `ncols` accumulator columns of this thread's TMEM lane into the activation block, software
+// pipelined over 16-column sub-chunks: the tcgen05.ld and the bias loads of sub-chunk i+1 are in flight
+// while sub-chunk i is converted and stored.
+template <bool RELU, bool ALPHA>
+__device__ __forceinline__ void epi_step(uint32_t t_lane, int ncols, const float* sbias, const float (&aw)[8], float& alpha,
+                                         uint8_t* act, int row) {
+  uint32_t v0[16], v1[16];
+  float4 b0[4], b1[4];
+  tmem_ld16(t_lane, v0);
+  load_bias16(b0, sbias);
+#pragma unroll 1
+  for (int c = 0; c < ncols; c += 32) {
+    tmem_wait_ld();
+    tmem_ld16(t_lane + c + 16, v1);
+    load_bias16(b1, sbias + c + 16);
+    epi_sub16<RELU, ALPHA>(v0, b0, aw, c, alpha, act, row);
+    tmem_wait_ld();
+    if (c + 32 < ncols) {
+      tmem_ld16(t_lane + c + 32, v0);
+      load_bias16(b0, sbias + c + 32);
+    }
+    epi_sub16<RELU, ALPHA>(v1, b1, aw, c + 16, alpha, act, row);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
-template <int kPair, bool kConst>
+template <int kPair>
 __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcParams P) {
   using C = TcCfg<kPair>;
   constexpr int NT = C::NT, NSLOT = C::NSLOT;
   extern __shared__ uint8_t smem_dyn[];
   // 1024-byte alignment (SWIZZLE_128B atoms); identical offset in both CTAs of a pair
+  // SWIZZLE_128B atoms need a 1024-byte aligned base (identical in both CTAs of a pair)
   const uint32_t raw_addr = smem_u32(smem_dyn);
-  uint8_t* smem = smem_dyn + ((1024 - (raw_addr & 1023)) & 1023);
+  const uint32_t pad = (1024 - (raw_addr & 1023)) & 1023;
+  if (pad > C::SMEM_SLACK) __trap();
+  uint8_t* smem = smem_dyn + pad;
   const uint32_t sbase = smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -423,7 +461,13 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
     uint8_t* act = smem + C::OFF_ACT + t * 4 * TC_KB_BYTES;
     uint8_t* pebuf = smem + C::OFF_PE;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + t * 256;
-    const TcBias bsrc{P.bias, P.cslot * TC_BIAS_FLOATS};
+    float* sbias = reinterpret_cast<float*>(smem + C::OFF_BIAS + t * 1024);
+    const int wg_tid = (warp - 2 - 4 * t) * 32 + lane;                       // 0..127 inside the warpgroup
+    float aw[8];                                                             // alpha weights 8*lane .. 8*lane+7
+#pragma unroll
+    for (int k = 0; k < 8; ++k) aw[k] = __ldg(P.bias + 11 * TC_BIAS_STRIDE + 8 * lane + k);
+    const float4 rgb_bias = __ldg(reinterpret_cast<const float4*>(P.bias + 10 * TC_BIAS_STRIDE));   // + alpha bias in .w
+    float2 next_bias = __ldg(reinterpret_cast<const float2*>(P.bias) + wg_tid);                      // row 0
     uint32_t nstep = 0;
 
     auto publish = [&]() {                          // A operand ready + accumulator drained
@@ -439,20 +483,30 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
       if (u > 0) mbar_wait(bar_pefree, (uint32_t)((u - 1) & 1));
     };
 
-    for (long long round = 0; round < n_rounds; ++round) {
-      const long long tile = (round * n_pairs + pair_id) * NT + t;
-      const long long i = (tile * kPair + rank) * 128 + row;          // global sample index
-      const bool valid = tile < P.n_tiles && i < P.in.n;
-      uint32_t pe_pos[32], pe_dir[16];
-      {
-        float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
-        if (valid) nm_fetch_sample(P.in, i, p, v);
-        encode_f16(P.pos_pe, p, pe_pos, 30);
-        uint32_t tmp[32];
-        encode_f16(P.dir_pe, v, tmp, 12);
+    // The encodings live in registers.  The position encoding of the NEXT tile is computed in the shadow of
+    // step 6's MMAs (its registers are dead after step 5), the direction encoding of the current tile in
+    // the shadow of step 7's, so only the very first tile pays for them on the critical path.
+    auto sample_index = [&](long long round) { return (((round * n_pairs + pair_id) * NT + t) * kPair + rank) * 128 + row; };
+    auto tile_valid = [&](long long round) { return ((round * n_pairs + pair_id) * NT + t) < P.n_tiles && sample_index(round) < P.in.n; };
+    uint32_t pe_pos[32], pe_dir[16];
+    auto encode_pos = [&](long long round) {
+      float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
+      if (tile_valid(round)) nm_fetch_sample(P.in, sample_index(round), p, v);
+      encode_f16(P.pos_pe, p, pe_pos, 30);
+    };
+    auto encode_dir = [&](long long round) {
+      float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
+      if (tile_valid(round)) nm_fetch_sample(P.in, sample_index(round), p, v);
+      uint32_t tmp[32];
+      encode_f16(P.dir_pe, v, tmp, 12);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pe_dir[j] = tmp[j];
-      }
+      for (int j = 0; j < 16; ++j) pe_dir[j] = tmp[j];
+    };
+    if (n_rounds > 0) encode_pos(0);
+
+    for (long long round = 0; round < n_rounds; ++round) {
+      const long long i = sample_index(round);                        // global sample index
+      const bool valid = tile_valid(round);
       // ---- step 0 input: positional encoding block ----
       wait_pe_slot(round, 0);
       store_row_swizzled(pebuf, row, pe_pos, 8);
@@ -462,31 +516,26 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
         mbar_wait(bar_tfull(t), nstep & 1);
         tc_fence_after();
         if (s < 10) {
-          const int niter = step_N(s) >> 5;               // 8 or 4 chunks of 32 columns
-          const bool relu = (s != 8);
-          // software pipeline: the tcgen05.ld of chunk it+1 is in flight while chunk it is processed
-          uint32_t va[32], vb[32];
-          tmem_ld32(t_lane, va);
-#pragma unroll 1
-          for (int it = 0; it < niter; it += 2) {
-            tmem_wait_ld();
-            tmem_ld32(t_lane + (it + 1) * 32, vb);
-            epi_chunk<kConst>(va, bsrc, s, it * 32, relu, alpha, act, row);
-            tmem_wait_ld();
-            if (it + 2 < niter) tmem_ld32(t_lane + (it + 2) * 32, va);
-            epi_chunk<kConst>(vb, bsrc, s, (it + 1) * 32, relu, alpha, act, row);
-          }
+          // this step's bias row -> the warpgroup's buffer (every warp of the group is past step s-1 here,
+          // because the accumulator of step s cannot be complete before all of them published step s-1)
+          reinterpret_cast<float2*>(sbias)[wg_tid] = next_bias;
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
+          if (s == 7) epi_step<true, true>(t_lane, 256, sbias, aw, alpha, act, row);
+          else if (s == 8) epi_step<false, false>(t_lane, 256, sbias, aw, alpha, act, row);
+          else epi_step<true, false>(t_lane, s == 9 ? 128 : 256, sbias, aw, alpha, act, row);
           if (s == 4) { wait_pe_slot(round, 1); store_row_swizzled(pebuf, row, pe_pos, 8); }    // skip input (:131)
           if (s == 8) { wait_pe_slot(round, 2); store_row_swizzled(pebuf, row, pe_dir, 4); }    // view dirs (:137)
           publish();
+          next_bias = __ldg(reinterpret_cast<const float2*>(P.bias + ((s + 1) % 10) * TC_BIAS_STRIDE) + wg_tid);
+          if (s == 5 && round + 1 < n_rounds) encode_pos(round + 1);
+          if (s == 6) encode_dir(round);
         } else {
           uint32_t v[4];
           tmem_ld4(t_lane + 128, v);
           tmem_wait_ld();
           if (valid) {
-            const float4 rb = bsrc.template ld<kConst>(10 * (TC_BIAS_STRIDE / 4));     // rgb bias (3) + alpha bias
-            float4 o = make_float4(__uint_as_float(v[0]) + rb.x, __uint_as_float(v[1]) + rb.y,
-                                   __uint_as_float(v[2]) + rb.z, alpha + rb.w);
+            float4 o = make_float4(__uint_as_float(v[0]) + rgb_bias.x, __uint_as_float(v[1]) + rgb_bias.y,
+                                   __uint_as_float(v[2]) + rgb_bias.z, alpha + rgb_bias.w);
             reinterpret_cast<float4*>(P.raw)[i] = o;                       // [r,g,b,sigma] (:144)
           }
           tc_fence_before();
@@ -606,19 +655,16 @@ int nm_tc_pack(nm_ctx* ctx, NmNet& net, cudaStream_t st) {
   k_tc_bias<<<1, 256, 0, st>>>(d.pts_b[0], d.pts_b[1], d.pts_b[2], d.pts_b[3], d.pts_b[4], d.pts_b[5], d.pts_b[6],
                                d.pts_b[7], d.feature_b, d.views_b, d.rgb_b, d.alpha_w, d.alpha_b, net.tc_bias);
   NM_CHECK_LAUNCH(ctx);
-  const int slot = (int)(&net - ctx->nets);
-  if (slot >= 0 && slot < TC_CONST_NETS)
-    NM_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tc_bias, net.tc_bias, TC_BIAS_FLOATS * sizeof(float),
-                                               (size_t)slot * TC_BIAS_FLOATS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
   return NM_OK;
 }
 
-template <int kPair, bool kConst>
+template <int kPair>
 static int launch_tc(nm_ctx* ctx, const TcParams& P, cudaStream_t st) {
   using C = TcCfg<kPair>;
   static bool attr_set = false;
   if (!attr_set) {
-    NM_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_mlp_tc<kPair, kConst>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    NM_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_mlp_tc<kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   int ctas = ctx->sm_count - (ctx->sm_count % kPair);
@@ -636,7 +682,7 @@ static int launch_tc(nm_ctx* ctx, const TcParams& P, cudaStream_t st) {
   attr[0].val.clusterDim.x = kPair; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NM_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_mlp_tc<kPair, kConst>, P));
+  NM_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_mlp_tc<kPair>, P));
   NM_LAUNCHED(ctx);
   return NM_OK;
 }
@@ -654,8 +700,5 @@ int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* 
   P.dir_pe = NmPeSpec{net.desc.dir_pe_kind, net.desc.dir_n_freqs, net.f32 + net.o_dir_bv};
   P.raw = raw;
   P.n_tiles = (n + 128 * kpair - 1) / (128 * kpair);
-  const int slot = (int)(&net - ctx->nets);
-  P.cslot = (slot >= 0 && slot < TC_CONST_NETS) ? slot : -1;
-  if (P.cslot >= 0) return kpair == 2 ? launch_tc<2, true>(ctx, P, st) : launch_tc<1, true>(ctx, P, st);
-  return kpair == 2 ? launch_tc<2, false>(ctx, P, st) : launch_tc<1, false>(ctx, P, st);
+  return kpair == 2 ? launch_tc<2>(ctx, P, st) : launch_tc<1>(ctx, P, st);
 }
