@@ -213,6 +213,12 @@ def main():
         flops_per_launch = prof["mlp_evals"] / max(prof["mlp_launches"], 1) * FLOP_PER_EVAL
         achieved = flops_per_launch / (mlp_ms_per_launch * 1e-3) / 1e12 if prof["mlp_ms"] > 0 else None
         peak = pk["tflops_sustained"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "mlp_tc_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            # DRAM bytes of one ncu-captured launch, scaled to this run's evaluations per launch
+            traffic = tj["dram_bytes_per_launch"] / tj["evals_per_launch"] * (prof["mlp_evals"] / max(prof["mlp_launches"], 1))
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -220,7 +226,8 @@ def main():
             "config": {"workload": WORKLOAD, "global_rays_per_step": n_pix, "mlp_evals_per_ray": EVALS_PER_RAY,
                        "parallelism": f"ray-shard x{world} + 1 all_gather", "l2": "per-step working set (raw [32768x256x4] f32 chunks, 3.8 GB/frame) >> 126 MB L2; no flush needed"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": None, "kernel": "k_mlp_tc<2>", "peak_source": pk["source"] + " bf16_tflops_sustained (fp16 runs at the bf16 rate)",
+                         "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write of one captured launch, scaled per evaluation; algorithmic 20 B/eval mostly stays in L2)",
+                         "kernel": "k_mlp_tc<2>", "peak_source": pk["source"] + " bf16_tflops_sustained (fp16 runs at the bf16 rate)",
                          "mlp_launches": prof["mlp_launches"], "mlp_ms_per_step": prof["mlp_ms"] / args.steps,
                          "mlp_share_of_step": prof["mlp_ms"] / ms_total},
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": 208, "d2h_bytes_per_step": n_pix * 4 * 4,

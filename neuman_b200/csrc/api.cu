@@ -142,6 +142,32 @@ static void pe_table(int kind, float fmin, float fmax, int nf, std::vector<float
     }
 }
 
+// Tables for the tensor-core path's range reduction "in cycles": every frequency (posenc) / projection row
+// (rotate) divided by 2*pi, split into a float hi + float lo pair (double precision source).
+static void pe_cycles_table(int kind, float fmin, float fmax, int nf, std::vector<float>& out) {
+  const double inv2pi = 0.15915494309189533576888;
+  std::vector<float> base;
+  pe_table(kind, fmin, fmax, nf, base);              // the float tables the reference semantics use
+  if (kind == NM_PE_POSENC) {
+    out.resize((size_t)nf * 2);
+    for (int k = 0; k < nf; ++k) {
+      double v = (double)base[k] * inv2pi;
+      float hi = (float)v;
+      out[2 * k] = hi;
+      out[2 * k + 1] = (float)(v - (double)hi);
+    }
+    return;
+  }
+  out.resize((size_t)nf * 3 * 6);
+  for (int q = 0; q < 3 * nf; ++q)
+    for (int i = 0; i < 3; ++i) {
+      double v = (double)base[(size_t)q * 3 + i] * inv2pi;
+      float hi = (float)v;
+      out[(size_t)q * 6 + i] = hi;
+      out[(size_t)q * 6 + 3 + i] = (float)(v - (double)hi);
+    }
+}
+
 extern "C" int nm_net_pack(nm_ctx* ctx, int slot, const nm_nerf_desc* d, void* stream) {
   if (!ctx) return NM_ERR_INVALID;
   if (slot < 0 || slot >= NM_MAX_NET_SLOTS || !d) NM_FAIL(ctx, NM_ERR_INVALID, "nm_net_pack: bad slot/desc");
@@ -168,6 +194,7 @@ extern "C" int nm_net_pack(nm_ctx* ctx, int slot, const nm_nerf_desc* d, void* s
     n.o_views_w = take((size_t)(NM_WIDTH + NM_DIR_PE) * NM_VIEWS_HID); n.o_views_b = take(NM_VIEWS_HID);
     n.o_rgb_w = take((size_t)NM_VIEWS_HID * 3); n.o_rgb_b = take(3);
     n.o_pos_bv = take(128); n.o_dir_bv = take(128);
+    n.o_pos_cyc = take(192); n.o_dir_cyc = take(192);
     n.f32_floats = off;
     NM_CHECK_CUDA(ctx, cudaMalloc(&n.f32, off * sizeof(float)));
   }
@@ -201,6 +228,14 @@ extern "C" int nm_net_pack(nm_ctx* ctx, int slot, const nm_nerf_desc* d, void* s
   NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));   // tab is a stack temporary
   pe_table(d->dir_pe_kind, d->dir_min_freq, d->dir_max_freq, d->dir_n_freqs, tab);
   NM_CHECK_CUDA(ctx, cudaMemcpyAsync(n.f32 + n.o_dir_bv, tab.data(), tab.size() * sizeof(float),
+                                     cudaMemcpyHostToDevice, st));
+  NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+  pe_cycles_table(d->pos_pe_kind, d->pos_min_freq, d->pos_max_freq, d->pos_n_freqs, tab);
+  NM_CHECK_CUDA(ctx, cudaMemcpyAsync(n.f32 + n.o_pos_cyc, tab.data(), tab.size() * sizeof(float),
+                                     cudaMemcpyHostToDevice, st));
+  NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+  pe_cycles_table(d->dir_pe_kind, d->dir_min_freq, d->dir_max_freq, d->dir_n_freqs, tab);
+  NM_CHECK_CUDA(ctx, cudaMemcpyAsync(n.f32 + n.o_dir_cyc, tab.data(), tab.size() * sizeof(float),
                                      cudaMemcpyHostToDevice, st));
   NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
   int rc = nm_tc_pack(ctx, n, st);

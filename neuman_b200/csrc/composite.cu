@@ -85,8 +85,8 @@ extern "C" int nm_raw2outputs(nm_ctx* ctx, const float* raw, const float* z, con
                               int32_t S, const float* noise, float sigma_scale, int32_t white_bkg, float* rgb,
                               float* disp, float* acc, float* weights, float* depth, void* stream) {
   if (!ctx) return NM_ERR_INVALID;
-  if (!raw || !z || !rays_d || R < 0 || S <= 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_raw2outputs: bad argument");
   if (R == 0) return NM_OK;
+  if (!raw || !z || !rays_d || R < 0 || S <= 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_raw2outputs: bad argument");
   unsigned blocks = (unsigned)((R * 32 + 255) / 256);
   k_raw2outputs<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)raw, z, rays_d, R, S, noise, sigma_scale,
                                                             white_bkg, rgb, disp, acc, weights, depth);
@@ -141,9 +141,9 @@ extern "C" int nm_merge_samples(nm_ctx* ctx, int32_t n_lists, const float* const
                                 const float* const* raw_lists, const int32_t* S_list, int64_t R, float* z_out,
                                 float* raw_out, void* stream) {
   if (!ctx) return NM_ERR_INVALID;
+  if (R == 0) return NM_OK;
   if (n_lists < 1 || n_lists > 1 + NM_MAX_ACTORS || !z_lists || !S_list || !z_out || R < 0)
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_merge_samples: bad argument");
-  if (R == 0) return NM_OK;
   MergeParams p;
   p.n_lists = n_lists;
   p.total = 0;

@@ -216,9 +216,19 @@ struct TcParams {
   long long n_tiles;        // number of (pair-)tiles
 };
 
-__device__ __noinline__ void nm_sincos(float a, float* s, float* c) { sincosf(a, s, c); }
+// sin/cos of 2*pi*f (f in cycles).  The operands of the tensor-core path are fp16 (quantisation 2.4e-4 on a
+// [-1,1] value), so the encodings only need ~1e-5: range reduction is done exactly in "cycles" with a
+// two-float 1/(2*pi) scale (error-free products via fma), then MUFU sin/cos on [-pi, pi] (abs err ~4e-7).
+__device__ __forceinline__ void sincos_cycles(float f, float& s, float& c) {
+  f = f - rintf(f);
+  const float a = f * 6.283185307179586f;
+  s = __sinf(a);
+  c = __cosf(a);
+}
 
 // Encodes x (3) into 64 f16 channels packed as 32 x f16x2; unused channels are zero.
+// pe.table for this path: posenc [n_freqs][2] = (hi, lo) of f_k/(2*pi); rotate [3 n_freqs][6] = (hi[3], lo[3])
+// of bvals[q]/(2*pi)  (api.cu: pe_cycles_table).
 __device__ __forceinline__ void encode_f16(const NmPeSpec& pe, const float x[3], uint32_t (&out)[32], int nq) {
   float ch[64];
 #pragma unroll
@@ -228,10 +238,17 @@ __device__ __forceinline__ void encode_f16(const NmPeSpec& pe, const float x[3],
 #pragma unroll
     for (int q = 0; q < 30; ++q) {
       if (q < nq) {
-        const float* b = pe.table + 3 * q;
-        float arg = fmaf(x[2], __ldg(b + 2), fmaf(x[1], __ldg(b + 1), x[0] * __ldg(b)));
+        const float* b = pe.table + 6 * q;
+        float frac = 0.f, low = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float bh = __ldg(b + i), bl = __ldg(b + 3 + i);
+          const float pr = x[i] * bh;
+          low += fmaf(x[i], bl, fmaf(x[i], bh, -pr));        // exact product residual + low part
+          frac += pr - rintf(pr);                            // exact
+        }
         float s, c;
-        nm_sincos(arg, &s, &c);
+        sincos_cycles(frac + low, s, c);
         if (nq == 30) { ch[3 + q] = s; ch[33 + q] = c; }
         else { ch[3 + q] = s; ch[15 + q] = c; }
       }
@@ -240,11 +257,13 @@ __device__ __forceinline__ void encode_f16(const NmPeSpec& pe, const float x[3],
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
       if (3 * k < nq) {
-        float f = __ldg(pe.table + k);
+        const float fh = __ldg(pe.table + 2 * k), fl = __ldg(pe.table + 2 * k + 1);
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
+          const float pr = x[d] * fh;
+          const float low = fmaf(x[d], fl, fmaf(x[d], fh, -pr));
           float s, c;
-          nm_sincos(x[d] * f, &s, &c);
+          sincos_cycles((pr - rintf(pr)) + low, s, c);
           ch[3 + 6 * k + d] = s; ch[6 + 6 * k + d] = c;
         }
       }
@@ -290,7 +309,7 @@ __device__ __forceinline__ void load_bias16(float4 (&b)[4], const float* sbias) 
 // 16 accumulator columns [c0, c0+16) of one row: +bias, (alpha head), ReLU, pack, two swizzled 16-byte stores
 template <bool RELU, bool ALPHA>
 __device__ __forceinline__ void epi_sub16(const uint32_t (&v)[16], const float4 (&b)[4], const float (&aw)[8], int c0,
-                                          float& alpha, uint8_t* act, int row) {
+                                          float (&alpha)[4], uint8_t* act, int row) {
   uint32_t packed[8];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -299,10 +318,10 @@ __device__ __forceinline__ void epi_sub16(const uint32_t (&v)[16], const float4 
     if (ALPHA) {                                // alpha_linear on the fp32 ReLU output (:135)
       // column c = c0 + 4g + j lives in lane c/8, register c%8
       const int src = (c0 >> 3) + (g >> 1), r0 = (g & 1) * 4;
-      alpha = fmaf(fmaxf(x0, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 0], src), alpha);
-      alpha = fmaf(fmaxf(x1, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 1], src), alpha);
-      alpha = fmaf(fmaxf(x2, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 2], src), alpha);
-      alpha = fmaf(fmaxf(x3, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 3], src), alpha);
+      alpha[0] = fmaf(fmaxf(x0, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 0], src), alpha[0]);
+      alpha[1] = fmaf(fmaxf(x1, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 1], src), alpha[1]);
+      alpha[2] = fmaf(fmaxf(x2, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 2], src), alpha[2]);
+      alpha[3] = fmaf(fmaxf(x3, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 3], src), alpha[3]);
     }
     packed[2 * g] = pack2<RELU>(x0, x1);
     packed[2 * g + 1] = pack2<RELU>(x2, x3);
@@ -317,7 +336,7 @@ __device__ __forceinline__ void epi_sub16(const uint32_t (&v)[16], const float4 
 // pipelined over 16-column sub-chunks: the tcgen05.ld and the bias loads of sub-chunk i+1 are in flight
 // while sub-chunk i is converted and stored.
 template <bool RELU, bool ALPHA>
-__device__ __forceinline__ void epi_step(uint32_t t_lane, int ncols, const float* sbias, const float (&aw)[8], float& alpha,
+__device__ __forceinline__ void epi_step(uint32_t t_lane, int ncols, const float* sbias, const float (&aw)[8], float (&alpha)[4],
                                          uint8_t* act, int row) {
   uint32_t v0[16], v1[16];
   float4 b0[4], b1[4];
@@ -511,7 +530,7 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
       wait_pe_slot(round, 0);
       store_row_swizzled(pebuf, row, pe_pos, 8);
       publish();
-      float alpha = 0.f;
+      float alpha[4] = {0.f, 0.f, 0.f, 0.f};
       for (int s = 0; s < TC_STEPS; ++s, ++nstep) {
         mbar_wait(bar_tfull(t), nstep & 1);
         tc_fence_after();
@@ -535,7 +554,7 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
           tmem_wait_ld();
           if (valid) {
             float4 o = make_float4(__uint_as_float(v[0]) + rgb_bias.x, __uint_as_float(v[1]) + rgb_bias.y,
-                                   __uint_as_float(v[2]) + rgb_bias.z, alpha + rgb_bias.w);
+                                   __uint_as_float(v[2]) + rgb_bias.z, (alpha[0] + alpha[1]) + (alpha[2] + alpha[3]) + rgb_bias.w);
             reinterpret_cast<float4*>(P.raw)[i] = o;                       // [r,g,b,sigma] (:144)
           }
           tc_fence_before();
@@ -696,8 +715,8 @@ int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* 
   P.bias = net.tc_bias;
   P.plan = make_plan(kpair);
   P.in = NmMlpInput{pts, views, origins, dirs, z, (long long)n, group};
-  P.pos_pe = NmPeSpec{net.desc.pos_pe_kind, net.desc.pos_n_freqs, net.f32 + net.o_pos_bv};
-  P.dir_pe = NmPeSpec{net.desc.dir_pe_kind, net.desc.dir_n_freqs, net.f32 + net.o_dir_bv};
+  P.pos_pe = NmPeSpec{net.desc.pos_pe_kind, net.desc.pos_n_freqs, net.f32 + net.o_pos_cyc};
+  P.dir_pe = NmPeSpec{net.desc.dir_pe_kind, net.desc.dir_n_freqs, net.f32 + net.o_dir_cyc};
   P.raw = raw;
   P.n_tiles = (n + 128 * kpair - 1) / (128 * kpair);
   return kpair == 2 ? launch_tc<2>(ctx, P, st) : launch_tc<1>(ctx, P, st);

@@ -26,7 +26,7 @@ struct NmNet {
   size_t f32_floats = 0;
   // offsets (in floats) into f32
   size_t o_pts_w[8], o_pts_b[8], o_feat_w, o_feat_b, o_alpha_w, o_alpha_b, o_views_w, o_views_b,
-      o_rgb_w, o_rgb_b, o_pos_bv, o_dir_bv;
+      o_rgb_w, o_rgb_b, o_pos_bv, o_dir_bv, o_pos_cyc, o_dir_cyc;
   // tensor-core layout (see mlp_tc.cu for the tile format)
   __half* f16 = nullptr;
   size_t f16_halfs = 0;

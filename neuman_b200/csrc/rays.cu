@@ -68,9 +68,9 @@ static void invert3x3(const double* m, double* o) {
 extern "C" int nm_raygen(nm_ctx* ctx, const nm_camera* cam, int mode, int64_t pix0, int64_t n,
                          const int32_t* xy, float* origins, float* dirs, void* stream) {
   if (!ctx) return NM_ERR_INVALID;
+  if (n == 0) return NM_OK;
   if (!cam || !origins || !dirs || n < 0 || (mode != 0 && mode != 1))
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_raygen: bad argument");
-  if (n == 0) return NM_OK;
   RaygenParams p;
   invert3x3(cam->K, p.Kinv);
   for (int i = 0; i < 16; ++i) p.c2w[i] = cam->c2w[i];
@@ -129,9 +129,9 @@ extern "C" int nm_near_far(nm_ctx* ctx, const float* origins, const float* dirs,
                            const float* verts, int32_t n_verts, float geo_threshold, float* near_out,
                            float* far_out, void* stream) {
   if (!ctx) return NM_ERR_INVALID;
+  if (R == 0) return NM_OK;
   if (!origins || !dirs || !verts || !near_out || !far_out || R < 0 || n_verts < 0)
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_near_far: bad argument");
-  if (R == 0) return NM_OK;
   // geo_threshold**2 is a python double that torch casts to f32 for the subtraction (:213)
   float thr2 = (float)((double)geo_threshold * (double)geo_threshold);
   unsigned blocks = (unsigned)((R + 127) / 128);
@@ -184,9 +184,9 @@ extern "C" int nm_ray_to_samples(nm_ctx* ctx, const float* origins, const float*
                                  int32_t lindisp, const float* t_rand, float* pts, float* dirs_out, float* z,
                                  void* stream) {
   if (!ctx) return NM_ERR_INVALID;
+  if (R == 0) return NM_OK;
   if (R < 0 || S <= 0 || ((pts || dirs_out) && (!origins || !dirs)))
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_ray_to_samples: bad argument");
-  if (R == 0) return NM_OK;
   long long total = (long long)R * S;
   unsigned blocks = (unsigned)((total + 255) / 256);
   k_ray_to_samples<<<blocks, 256, 0, (cudaStream_t)stream>>>(origins, dirs, near_v, far_v, near_s, far_s, R, S,

@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_sample_pdf(const float* __res
 extern "C" int nm_sample_pdf(nm_ctx* ctx, const float* bins, const float* weights, int64_t R, int32_t B, int32_t N,
                              const float* u, float* out, void* stream) {
   if (!ctx) return NM_ERR_INVALID;
-  if (!bins || !weights || !out || R < 0 || B < 2 || N <= 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_sample_pdf: bad argument");
   if (R == 0) return NM_OK;
+  if (!bins || !weights || !out || R < 0 || B < 2 || N <= 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_sample_pdf: bad argument");
   size_t smem = (size_t)RS_WARPS * 2 * B * sizeof(float);
   if (smem > 48 * 1024) NM_FAIL(ctx, NM_ERR_UNSUPPORTED, "nm_sample_pdf: too many bins");
   unsigned blocks = (unsigned)((R + RS_WARPS - 1) / RS_WARPS);
@@ -133,9 +133,9 @@ extern "C" int nm_importance_samples(nm_ctx* ctx, const float* origins, const fl
                                      const float* weights, int64_t R, int32_t S, int32_t N, int32_t including_old,
                                      float* pts, float* dirs_out, float* z_out, void* stream) {
   if (!ctx) return NM_ERR_INVALID;
+  if (R == 0) return NM_OK;
   if (!z || !weights || !z_out || R < 0 || S < 3 || N <= 0 || ((pts || dirs_out) && (!origins || !dirs)))
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_importance_samples: bad argument (needs S >= 3)");
-  if (R == 0) return NM_OK;
   int total = including_old ? S + N : N;
   int pow2 = 32;
   while (pow2 < total) pow2 <<= 1;

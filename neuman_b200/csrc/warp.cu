@@ -326,9 +326,9 @@ extern "C" int nm_mesh_set(nm_ctx* ctx, int actor, const float* verts, int32_t n
 extern "C" int nm_warp_to_canonical(nm_ctx* ctx, int actor, const float* pts, int64_t R, int32_t S, float* can_pts,
                                     float* can_dirs, float* closest, int32_t* face_id, void* stream) {
   if (!ctx) return NM_ERR_INVALID;
+  if (R == 0) return NM_OK;
   if (actor < 0 || actor >= NM_MAX_ACTORS || !ctx->meshes[actor].set) NM_FAIL(ctx, NM_ERR_STATE, "nm_warp_to_canonical: mesh not set");
   if (!pts || !can_pts || R < 0 || S <= 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_warp_to_canonical: bad argument");
-  if (R == 0) return NM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   NmMesh& m = ctx->meshes[actor];
   long long n = (long long)R * S;
