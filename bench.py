@@ -147,7 +147,7 @@ def main():
     import neuman_b200 as nb
     from neuman_b200 import render, sharding
     from neuman_b200._lib import Context
-    from oracle import scenes          # seeded synthetic inputs only (camera, weight seeds)
+    from neuman_b200 import synthetic as scenes     # seeded synthetic inputs (camera, weight seeds)
     coarse, fine = scenes.seed_nets(nb.build_nerf, nb.default_opt(use_cuda=False), 1)
     coarse, fine = coarse.to(dev), fine.to(dev)
     K, c2w = scenes.camera(H, W, seed=1)
