@@ -191,7 +191,7 @@ struct TcCfg {
   static constexpr int NT = kPair == 2 ? 2 : 1;
   static constexpr int NSLOT = kPair == 2 ? 5 : 4;
   static constexpr int SLOT_BYTES = 32768 / kPair;
-  static constexpr int THREADS = 64 + 128 * NT;
+  static constexpr int THREADS = 64 + 256;        // producer + MMA warps, 8 epilogue warps
   static constexpr int OFF_ACT = 0;
   static constexpr int OFF_PE = OFF_ACT + NT * 4 * TC_KB_BYTES;
   static constexpr int OFF_RING = OFF_PE + TC_KB_BYTES;
@@ -201,7 +201,7 @@ struct TcCfg {
   static constexpr int OFF_TMEMPTR = OFF_BAR + 8 * N_BAR;
   // per-warpgroup copy of the current step's bias row (256 fp32), refreshed each step by the warpgroup
   static constexpr int OFF_BIAS = (OFF_TMEMPTR + 16 + 127) & ~127;
-  static constexpr int SMEM_USED = OFF_BIAS + NT * 1024;
+  static constexpr int SMEM_USED = OFF_BIAS + 1024 + NT * 512;   // bias row + alpha partials
   static constexpr int SMEM_SLACK = (232448 - SMEM_USED) < 1024 ? (232448 - SMEM_USED) : 1024;   // alignment slack that still fits 227 KB
   static constexpr int SMEM_BYTES = SMEM_USED + SMEM_SLACK;
 };
@@ -214,6 +214,7 @@ struct TcParams {
   NmPeSpec pos_pe, dir_pe;
   float* raw;
   long long n_tiles;        // number of (pair-)tiles
+  long long* trace;         // optional debug timeline (tools/tc_trace.py): [cta<2][role<2][event<4][256] clock64 stamps
 };
 
 // sin/cos of 2*pi*f (f in cycles).  The operands of the tensor-core path are fp16 (quantisation 2.4e-4 on a
@@ -336,20 +337,20 @@ __device__ __forceinline__ void epi_sub16(const uint32_t (&v)[16], const float4 
 // pipelined over 16-column sub-chunks: the tcgen05.ld and the bias loads of sub-chunk i+1 are in flight
 // while sub-chunk i is converted and stored.
 template <bool RELU, bool ALPHA>
-__device__ __forceinline__ void epi_step(uint32_t t_lane, int ncols, const float* sbias, const float (&aw)[8], float (&alpha)[4],
-                                         uint8_t* act, int row) {
+__device__ __forceinline__ void epi_step(uint32_t t_lane, int cbase, int ncols, const float* sbias, const float (&aw)[8],
+                                         float (&alpha)[4], uint8_t* act, int row) {
   uint32_t v0[16], v1[16];
   float4 b0[4], b1[4];
-  tmem_ld16(t_lane, v0);
-  load_bias16(b0, sbias);
+  tmem_ld16(t_lane + cbase, v0);
+  load_bias16(b0, sbias + cbase);
 #pragma unroll 1
-  for (int c = 0; c < ncols; c += 32) {
+  for (int c = cbase; c < cbase + ncols; c += 32) {
     tmem_wait_ld();
     tmem_ld16(t_lane + c + 16, v1);
     load_bias16(b1, sbias + c + 16);
     epi_sub16<RELU, ALPHA>(v0, b0, aw, c, alpha, act, row);
     tmem_wait_ld();
-    if (c + 32 < ncols) {
+    if (c + 32 < cbase + ncols) {
       tmem_ld16(t_lane + c + 32, v0);
       load_bias16(b0, sbias + c + 32);
     }
@@ -360,6 +361,13 @@ __device__ __forceinline__ void epi_step(uint32_t t_lane, int ncols, const float
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
+// debug timeline: role 0 = MMA issuer (events 0: operand ready seen, 1: step issued+committed),
+// role 1 = epilogue warp 2 lane 0 (events 0: accumulator ready seen, 1: drained, 2: published); tile 0 only
+#define TC_TRACE(role, ev, idx)                                                                             \
+  do {                                                                                                      \
+    if (P.trace && blockIdx.x < 2 && (idx) < 256) P.trace[((blockIdx.x * 2 + (role)) * 4 + (ev)) * 256 + (idx)] = clock64(); \
+  } while (0)
+
 template <int kPair>
 __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcParams P) {
   using C = TcCfg<kPair>;
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_peer(i), 1); mbar_init(bar_empty(i), 1); }
-    for (int t = 0; t < NT; ++t) { mbar_init(bar_tfull(t), 1); mbar_init(bar_aready(t), 4 * kPair); }
+    for (int t = 0; t < NT; ++t) { mbar_init(bar_tfull(t), 1); mbar_init(bar_aready(t), 8 * kPair); }
     mbar_init(bar_pefree, 1);
     fence_mbar_init();
   }
@@ -425,37 +433,53 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
   } else if (warp == 1) {
     if (rank == 0) {
       // =============================== MMA issuer (leader CTA) ===============================
-      if (lane == 0) {
-        uint32_t q0 = 0, nstep = 0;
-        for (long long round = 0; round < n_rounds; ++round) {
-          for (int s = 0; s < TC_STEPS; ++s, ++nstep) {
-            const uint32_t idesc = make_idesc(128 * kPair, step_N(s));
-            const int nkb = step_nkb(s);
-            for (int t = 0; t < NT; ++t) {
-              mbar_wait(bar_aready(t), nstep & 1);          // A operand written, accumulator drained
-              tc_fence_after();
-              const uint32_t d_tmem = tmem_base + t * 256 + (s == 10 ? 128 : 0);
-              for (int kb = 0; kb < nkb; ++kb) {
-                const uint32_t q = q0 + kb, slot = q % NSLOT, gen = q / NSLOT;
-                if (t == 0) {
-                  mbar_wait(bar_full(slot), gen & 1);
-                  if (kPair == 2) mbar_wait(bar_peer(slot), gen & 1);
-                  tc_fence_after();
+      // The whole warp runs this loop with warp-uniform values (so descriptors stay in uniform registers and
+      // ptxas needs no divergence "waterfall" around UTCHMMA); one elected lane issues the tcgen05 instructions.
+      uint32_t issuer = 0;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t.reg .b32 r;\n\telect.sync r|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(issuer));
+      uint32_t q0 = 0, nstep = 0;
+      for (long long round = 0; round < n_rounds; ++round) {
+        for (int s = 0; s < TC_STEPS; ++s, ++nstep) {
+          const uint32_t idesc = make_idesc(128 * kPair, step_N(s));
+          const int nkb = step_nkb(s);
+          for (int t = 0; t < NT; ++t) {
+            mbar_wait(bar_aready(t), nstep & 1);          // A operand written, accumulator drained
+            tc_fence_after();
+            if (t == 0 && issuer) TC_TRACE(0, 0, nstep);
+            const uint32_t d_tmem = tmem_base + t * 256 + (s == 10 ? 128 : 0);
+            for (int kb = 0; kb < nkb; ++kb) {
+              const uint32_t q = q0 + kb, slot = q % NSLOT, gen = q / NSLOT;
+              if (t == 0) {
+                mbar_wait(bar_full(slot), gen & 1);
+                if (kPair == 2) mbar_wait(bar_peer(slot), gen & 1);
+                tc_fence_after();
+              }
+              const bool is_pe = kb_is_pe(s, kb);
+              const uint32_t a_addr = is_pe ? sbase + C::OFF_PE
+                                            : sbase + C::OFF_ACT + (t * 4 + kb_act_index(s, kb)) * TC_KB_BYTES;
+              const uint64_t a_desc = make_desc(a_addr);
+              const uint64_t b_desc = make_desc(sbase + C::OFF_RING + slot * C::SLOT_BYTES);
+              if (issuer) {
+                // K advances by 32 B (= 2 in descriptor address units) inside the 128-byte swizzle atom
+                umma_f16<kPair>(d_tmem, a_desc, b_desc, idesc, kb != 0);
+                umma_f16<kPair>(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
+                if (kb_ksteps(s, kb) == 4) {
+                  umma_f16<kPair>(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
+                  umma_f16<kPair>(d_tmem, a_desc + 6, b_desc + 6, idesc, 1);
                 }
-                const bool is_pe = kb_is_pe(s, kb);
-                const uint32_t a_addr = is_pe ? sbase + C::OFF_PE
-                                              : sbase + C::OFF_ACT + (t * 4 + kb_act_index(s, kb)) * TC_KB_BYTES;
-                const uint32_t b_addr = sbase + C::OFF_RING + slot * C::SLOT_BYTES;
-                const int nk = kb_ksteps(s, kb);
-                for (int j = 0; j < nk; ++j)
-                  umma_f16<kPair>(d_tmem, make_desc(a_addr + 32 * j), make_desc(b_addr + 32 * j), idesc, (kb | j) != 0);
                 if (t == NT - 1) umma_commit<kPair>(bar_empty(slot));      // slab consumed by every tile
                 if (is_pe) umma_commit<kPair>(bar_pefree);                 // PE block may be rewritten
               }
-              umma_commit<kPair>(bar_tfull(t));                            // accumulator complete
+              __syncwarp();
             }
-            q0 += nkb;
+            if (issuer) {
+              umma_commit<kPair>(bar_tfull(t));                            // accumulator complete
+              if (t == 0) TC_TRACE(0, 1, nstep);
+            }
+            __syncwarp();
           }
+          q0 += nkb;
         }
       }
     } else {
@@ -473,23 +497,26 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
       }
     }
   } else {
-    // =============================== epilogue warpgroups ===============================
-    const int t = (warp - 2) >> 2;                 // tile slot served by this warpgroup
+    // ========================= epilogue: 8 warps serve the tiles in flight in turn =========================
+    // Both warpgroups drain every tile: warp (2+q) and warp (6+q) share TMEM lane quadrant q and split the
+    // accumulator columns in halves (g = 0 / 1), so a step's epilogue takes half as long.  Warpgroup g also
+    // owns the encodings (registers) of tile g and stores them into the PE block at that tile's steps 0/5/9.
+    const int ew = warp - 2;                       // 0..7
+    const int g = ew >> 2;                         // column half; tile whose encodings this thread owns
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;              // sample row inside the CTA tile
-    uint8_t* act = smem + C::OFF_ACT + t * 4 * TC_KB_BYTES;
+    const int etid = ew * 32 + lane;               // 0..255
     uint8_t* pebuf = smem + C::OFF_PE;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + t * 256;
-    float* sbias = reinterpret_cast<float*>(smem + C::OFF_BIAS + t * 1024);
-    const int wg_tid = (warp - 2 - 4 * t) * 32 + lane;                       // 0..127 inside the warpgroup
-    float aw[8];                                                             // alpha weights 8*lane .. 8*lane+7
+    float* sbias = reinterpret_cast<float*>(smem + C::OFF_BIAS);           // current step's bias row (256 fp32)
+    float* s_alpha = sbias + 256;                                          // [NT][128] alpha partial of the g==1 half
+    float aw[8];                                                           // alpha weights 8*lane .. 8*lane+7
 #pragma unroll
     for (int k = 0; k < 8; ++k) aw[k] = __ldg(P.bias + 11 * TC_BIAS_STRIDE + 8 * lane + k);
     const float4 rgb_bias = __ldg(reinterpret_cast<const float4*>(P.bias + 10 * TC_BIAS_STRIDE));   // + alpha bias in .w
-    float2 next_bias = __ldg(reinterpret_cast<const float2*>(P.bias) + wg_tid);                      // row 0
     uint32_t nstep = 0;
 
-    auto publish = [&]() {                          // A operand ready + accumulator drained
+    auto epi_barrier = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    auto publish = [&](int t) {                     // tile t: A operand ready + accumulator drained
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -497,67 +524,91 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
     };
     // PE-buffer use index u (order of the MMA stream: per round A0,B0,A5,B5,A9,B9); the writer of use u
     // waits until the MMAs of use u-1 have retired
-    auto wait_pe_slot = [&](long long round, int k) {
+    auto wait_pe_slot = [&](long long round, int k, int t) {
       long long u = (round * 3 + k) * NT + t;
       if (u > 0) mbar_wait(bar_pefree, (uint32_t)((u - 1) & 1));
     };
-
-    // The encodings live in registers.  The position encoding of the NEXT tile is computed in the shadow of
-    // step 6's MMAs (its registers are dead after step 5), the direction encoding of the current tile in
-    // the shadow of step 7's, so only the very first tile pays for them on the critical path.
-    auto sample_index = [&](long long round) { return (((round * n_pairs + pair_id) * NT + t) * kPair + rank) * 128 + row; };
-    auto tile_valid = [&](long long round) { return ((round * n_pairs + pair_id) * NT + t) < P.n_tiles && sample_index(round) < P.in.n; };
+    auto sample_index = [&](long long round, int t) { return (((round * n_pairs + pair_id) * NT + t) * kPair + rank) * 128 + row; };
+    auto tile_valid = [&](long long round, int t) {
+      return ((round * n_pairs + pair_id) * NT + t) < P.n_tiles && sample_index(round, t) < P.in.n;
+    };
+    // The encodings of tile g live in this thread's registers.  The position encoding of the NEXT round is
+    // computed in the shadow of step 6's MMAs (its registers are dead after step 5), the direction encoding of
+    // the current round in the shadow of step 7's, so only the very first tile pays for them up front.
+    const bool pe_owner = g < NT;
     uint32_t pe_pos[32], pe_dir[16];
     auto encode_pos = [&](long long round) {
       float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
-      if (tile_valid(round)) nm_fetch_sample(P.in, sample_index(round), p, v);
+      if (tile_valid(round, g)) nm_fetch_sample(P.in, sample_index(round, g), p, v);
       encode_f16(P.pos_pe, p, pe_pos, 30);
     };
     auto encode_dir = [&](long long round) {
       float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
-      if (tile_valid(round)) nm_fetch_sample(P.in, sample_index(round), p, v);
+      if (tile_valid(round, g)) nm_fetch_sample(P.in, sample_index(round, g), p, v);
       uint32_t tmp[32];
       encode_f16(P.dir_pe, v, tmp, 12);
 #pragma unroll
       for (int j = 0; j < 16; ++j) pe_dir[j] = tmp[j];
     };
-    if (n_rounds > 0) encode_pos(0);
+    if (n_rounds > 0 && pe_owner) encode_pos(0);
+    sbias[etid] = __ldg(P.bias + etid);            // bias row of step 0
+    epi_barrier();
 
     for (long long round = 0; round < n_rounds; ++round) {
-      const long long i = sample_index(round);                        // global sample index
-      const bool valid = tile_valid(round);
-      // ---- step 0 input: positional encoding block ----
-      wait_pe_slot(round, 0);
-      store_row_swizzled(pebuf, row, pe_pos, 8);
-      publish();
-      float alpha[4] = {0.f, 0.f, 0.f, 0.f};
+      // ---- step 0 inputs: positional encoding blocks ----
+      for (int t = 0; t < NT; ++t) {
+        if (g == t) {
+          wait_pe_slot(round, 0, t);
+          store_row_swizzled(pebuf, row, pe_pos, 8);
+        }
+        publish(t);
+      }
+      float alpha[NT][4];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) alpha[t][0] = alpha[t][1] = alpha[t][2] = alpha[t][3] = 0.f;
       for (int s = 0; s < TC_STEPS; ++s, ++nstep) {
-        mbar_wait(bar_tfull(t), nstep & 1);
-        tc_fence_after();
-        if (s < 10) {
-          // this step's bias row -> the warpgroup's buffer (every warp of the group is past step s-1 here,
-          // because the accumulator of step s cannot be complete before all of them published step s-1)
-          reinterpret_cast<float2*>(sbias)[wg_tid] = next_bias;
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");
-          if (s == 7) epi_step<true, true>(t_lane, 256, sbias, aw, alpha, act, row);
-          else if (s == 8) epi_step<false, false>(t_lane, 256, sbias, aw, alpha, act, row);
-          else epi_step<true, false>(t_lane, s == 9 ? 128 : 256, sbias, aw, alpha, act, row);
-          if (s == 4) { wait_pe_slot(round, 1); store_row_swizzled(pebuf, row, pe_pos, 8); }    // skip input (:131)
-          if (s == 8) { wait_pe_slot(round, 2); store_row_swizzled(pebuf, row, pe_dir, 4); }    // view dirs (:137)
-          publish();
-          next_bias = __ldg(reinterpret_cast<const float2*>(P.bias + ((s + 1) % 10) * TC_BIAS_STRIDE) + wg_tid);
-          if (s == 5 && round + 1 < n_rounds) encode_pos(round + 1);
-          if (s == 6) encode_dir(round);
-        } else {
-          uint32_t v[4];
-          tmem_ld4(t_lane + 128, v);
-          tmem_wait_ld();
-          if (valid) {
-            float4 o = make_float4(__uint_as_float(v[0]) + rgb_bias.x, __uint_as_float(v[1]) + rgb_bias.y,
-                                   __uint_as_float(v[2]) + rgb_bias.z, (alpha[0] + alpha[1]) + (alpha[2] + alpha[3]) + rgb_bias.w);
-            reinterpret_cast<float4*>(P.raw)[i] = o;                       // [r,g,b,sigma] (:144)
+        const float next_bias = (s < 10) ? __ldg(P.bias + ((s + 1) % 10) * TC_BIAS_STRIDE + etid) : 0.f;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          uint8_t* act = smem + C::OFF_ACT + t * 4 * TC_KB_BYTES;
+          const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + t * 256;
+          mbar_wait(bar_tfull(t), nstep & 1);
+          tc_fence_after();
+          if (t == 0 && etid == 0) TC_TRACE(1, 0, nstep);
+          if (s < 10) {
+            const int nh = (s == 9) ? 64 : 128;         // columns drained by this thread
+            if (s == 7) epi_step<true, true>(t_lane, g * nh, nh, sbias, aw, alpha[t], act, row);
+            else if (s == 8) epi_step<false, false>(t_lane, g * nh, nh, sbias, aw, alpha[t], act, row);
+            else epi_step<true, false>(t_lane, g * nh, nh, sbias, aw, alpha[t], act, row);
+            if (s == 7 && g == 1) s_alpha[t * 128 + row] = (alpha[t][0] + alpha[t][1]) + (alpha[t][2] + alpha[t][3]);
+            if (s == 4 && g == t) { wait_pe_slot(round, 1, t); store_row_swizzled(pebuf, row, pe_pos, 8); }   // skip input (:131)
+            if (s == 8 && g == t) { wait_pe_slot(round, 2, t); store_row_swizzled(pebuf, row, pe_dir, 4); }   // view dirs (:137)
+            if (t == 0 && etid == 0) TC_TRACE(1, 1, nstep);
+            publish(t);
+            if (t == 0 && etid == 0) TC_TRACE(1, 2, nstep);
+          } else {
+            if (g == 0) {
+              uint32_t v[4];
+              tmem_ld4(t_lane + 128, v);
+              tmem_wait_ld();
+              const long long i = sample_index(round, t);
+              if (tile_valid(round, t)) {
+                const float a = (alpha[t][0] + alpha[t][1]) + (alpha[t][2] + alpha[t][3]) + s_alpha[t * 128 + row];
+                float4 o = make_float4(__uint_as_float(v[0]) + rgb_bias.x, __uint_as_float(v[1]) + rgb_bias.y,
+                                       __uint_as_float(v[2]) + rgb_bias.z, a + rgb_bias.w);
+                reinterpret_cast<float4*>(P.raw)[i] = o;                     // [r,g,b,sigma] (:144)
+              }
+            }
+            tc_fence_before();
           }
-          tc_fence_before();
+        }
+        if (s < 10) {
+          // next step's bias row: every epilogue thread is done reading the current one after this barrier
+          epi_barrier();
+          sbias[etid] = next_bias;
+          epi_barrier();
+          if (s == 5 && round + 1 < n_rounds && pe_owner) encode_pos(round + 1);
+          if (s == 6 && pe_owner) encode_dir(round);
         }
       }
     }
@@ -719,5 +770,7 @@ int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* 
   P.dir_pe = NmPeSpec{net.desc.dir_pe_kind, net.desc.dir_n_freqs, net.f32 + net.o_dir_cyc};
   P.raw = raw;
   P.n_tiles = (n + 128 * kpair - 1) / (128 * kpair);
+  P.trace = nullptr;
+  if (const char* e = getenv("NEUMAN_TC_TRACE")) P.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   return kpair == 2 ? launch_tc<2>(ctx, P, st) : launch_tc<1>(ctx, P, st);
 }
