@@ -151,6 +151,29 @@ int nm_warp_to_canonical(nm_ctx* ctx, int actor, const float* pts, int64_t R, in
                          float* can_pts, float* can_dirs, float* closest, int32_t* face_id,
                          void* stream);
 
+/* ---- SMPL per-vertex transforms: models/smpl.py:109-162,266-505; data_io/neuman_helper.py:299-330 ---- */
+typedef struct {
+  const float* v_template;   /* [V,3]      DEVICE  (models/smpl.py:81-83)  */
+  const float* shapedirs;    /* [V,3,NB]   DEVICE  (:86-88)                */
+  const float* J_regressor;  /* [J,V]      DEVICE  (:90-91)                */
+  const float* weights;      /* [V,J]      DEVICE  lbs_weights (:106-107)  */
+  const int32_t* parents;    /* [J]        HOST    kintree_table[0], parents[0] = -1 (:101-104) */
+  int32_t n_verts, n_joints, n_betas;
+} nm_smpl_model;
+
+/* SMPL.verts_transformations(poses, betas, concat_joints) (models/smpl.py:109-162), float32:
+ * pose [3*J], betas [NB] DEVICE -> T [V(+J),4,4], verts [V(+J),3] (v_shaped (+ joints); may be NULL). */
+int nm_smpl_vertex_transforms(nm_ctx* ctx, const nm_smpl_model* model, const float* pose, const float* betas,
+                              int32_t concat_joints, float* T, float* verts, void* stream);
+
+/* read_smpls / HumanNeRF.vertex_forward (data_io/neuman_helper.py:299-330, models/human_nerf.py:92-122):
+ * T_da2scene = S . alignment^T . T_t2pose . inv(T_t2da) as float64 [V+J,4,4] (the `Ts` the warp consumes) and
+ * world_verts = T_da2scene . da_pose_verts as float32 [V+J,3] (vertices then joints; may be NULL).
+ * pose, da_pose, betas DEVICE; alignment (4x4 row-major) HOST. */
+int nm_smpl_scene_transforms(nm_ctx* ctx, const nm_smpl_model* model, const float* pose, const float* da_pose,
+                             const float* betas, const double* alignment, double scale, double* T_da2scene,
+                             float* world_verts, void* stream);
+
 /* ---- frame drivers: utils/render_utils.py:108-461 ----------------------------------------- */
 typedef struct {
   int32_t samples_per_ray;              /* S */

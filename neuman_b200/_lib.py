@@ -37,6 +37,12 @@ class NmRenderOpts(C.Structure):
                 ("geo_threshold", C.c_float), ("interval_comp", C.c_float)]
 
 
+class NmSmplModel(C.Structure):
+    _fields_ = [("v_template", C.c_void_p), ("shapedirs", C.c_void_p), ("J_regressor", C.c_void_p),
+                ("weights", C.c_void_p), ("parents", C.POINTER(C.c_int32)),
+                ("n_verts", C.c_int32), ("n_joints", C.c_int32), ("n_betas", C.c_int32)]
+
+
 _P = C.c_void_p
 _I32, _I64, _F = C.c_int32, C.c_int64, C.c_float
 
@@ -59,6 +65,9 @@ SIGNATURES = {
     "nm_merge_samples": (C.c_int, [_P, _I32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I32), _I64, _P, _P, _P]),
     "nm_mesh_set": (C.c_int, [_P, C.c_int, _P, _I32, _P, _I32, _P, _I32, _I32, _P]),
     "nm_warp_to_canonical": (C.c_int, [_P, C.c_int, _P, _I64, _I32, _P, _P, _P, _P, _P]),
+    "nm_smpl_vertex_transforms": (C.c_int, [_P, C.POINTER(NmSmplModel), _P, _P, _I32, _P, _P, _P]),
+    "nm_smpl_scene_transforms": (C.c_int, [_P, C.POINTER(NmSmplModel), _P, _P, _P, C.POINTER(C.c_double), C.c_double,
+                                           _P, _P, _P]),
     "nm_render_vanilla": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(NmCamera), C.POINTER(NmRenderOpts), _I64, _I64,
                                     _P, _P, _I32, _P]),
     "nm_render_smpl_nerf": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(NmCamera), C.POINTER(NmRenderOpts), _I64, _I64,

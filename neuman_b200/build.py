@@ -23,6 +23,7 @@ SOURCES = {           # file -> extra flags
     "resample.cu": ["-fmad=false"],
     "render.cu": ["-fmad=false"],
     "warp.cu": [],
+    "smpl.cu": [],
     "mlp_simt.cu": [],
     "mlp_tc.cu": [],
 }

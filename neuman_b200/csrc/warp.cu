@@ -1,35 +1,48 @@
 // Observation -> canonical warp: closest point on the posed SMPL mesh, barycentric blend of the
 // three per-vertex 4x4 transforms, inverse, apply; canonical view directions by finite differences.
 //
-//   nm_mesh_set            per-frame inputs of warp_samples_to_canonical (verts, faces, T) + grid
+//   nm_mesh_set            per-frame inputs of warp_samples_to_canonical (verts, faces, T) + LBVH build
 //   nm_warp_to_canonical   <- utils/ray_utils.py:48-66 (igl.point_mesh_squared_distance :53,
 //                             igl.barycentric_coordinates_tri :55, blend :56, inverse :57, apply :58,
 //                             finite-difference directions :62-64)
 //
 // The reference does this stage on the CPU in float64 (libigl AABB tree) with a device->host->device
-// round trip per batch (utils/render_utils.py:218-227).  Here a per-frame uniform grid stores, for
-// every cell, the conservative list of triangles that can be the closest one for ANY point of the
-// cell (sphere bounds), so a query is one short exact scan.  The arg-min runs in fp32; the winning
-// triangle is then re-evaluated in float64 (closest point, barycentrics, blend, inverse, apply), which
-// is what the reference's float64 chain produces before `.float()` (utils/render_utils.py:226).
-#include <cub/device/device_scan.cuh>
+// round trip per batch (utils/render_utils.py:218-227).  Here a linear BVH (Morton-sorted triangles,
+// Karras 2012 hierarchy, bottom-up AABB refit) is rebuilt per frame (13 776 triangles: microseconds)
+// and every sample runs an exact nearest-triangle traversal (stack, nearer child first, prune by the
+// best squared distance).  The arg-min runs in fp32 (exact ties -> lowest face index); the winning
+// triangle is then re-evaluated in float64 (closest point, barycentrics, blend, inverse, apply),
+// which is what the reference's float64 chain produces before `.float()` (utils/render_utils.py:226).
+#include <cub/device/device_radix_sort.cuh>
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "nm_internal.cuh"
 
-#define GRID_MAX_DIM 64
-
-struct GridDesc {
-  float3 gmin;
-  float cell, inv_cell;
-  int3 dims;
-  int ncell;
+// ---------------------------------------------------------------------------------------------
+// LBVH build
+// ---------------------------------------------------------------------------------------------
+struct BvhView {
+  int n;                         // triangles (leaves); node ids: internal [0, n-1), leaf k -> n-1+k
+  const float4* lo;              // [2n-1] AABB min
+  const float4* hi;              // [2n-1] AABB max
+  const int2* children;          // [n-1]
+  const int32_t* leaf_face;      // [n]
+  const float* tri9;             // [F][9] packed triangle vertices
 };
 
-// ---------------------------------------------------------------------------------------------
-__global__ void k_tri_prepare(const float* __restrict__ verts, const int32_t* __restrict__ faces, int nf,
-                              float4* __restrict__ sphere, float* __restrict__ tri9) {
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+
+// packed triangles + Morton keys of the centroids (key = morton30 << 32 | face: unique)
+__global__ void k_bvh_keys(const float* __restrict__ verts, const int32_t* __restrict__ faces, int nf, float3 bmin,
+                           float3 binv, float* __restrict__ tri9, unsigned long long* __restrict__ keys) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= nf) return;
   float v[9];
@@ -38,61 +51,74 @@ __global__ void k_tri_prepare(const float* __restrict__ verts, const int32_t* __
     int vi = faces[3 * f + k];
     v[3 * k] = verts[3 * vi]; v[3 * k + 1] = verts[3 * vi + 1]; v[3 * k + 2] = verts[3 * vi + 2];
   }
-  float cx = (v[0] + v[3] + v[6]) / 3.f, cy = (v[1] + v[4] + v[7]) / 3.f, cz = (v[2] + v[5] + v[8]) / 3.f;
-  float r2 = 0.f;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    float dx = v[3 * k] - cx, dy = v[3 * k + 1] - cy, dz = v[3 * k + 2] - cz;
-    r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
-  }
-  sphere[f] = make_float4(cx, cy, cz, sqrtf(r2) * 1.0001f + 1e-7f);
 #pragma unroll
   for (int k = 0; k < 9; ++k) tri9[9 * f + k] = v[k];
+  float cx = ((v[0] + v[3] + v[6]) * (1.f / 3.f) - bmin.x) * binv.x;
+  float cy = ((v[1] + v[4] + v[7]) * (1.f / 3.f) - bmin.y) * binv.y;
+  float cz = ((v[2] + v[5] + v[8]) * (1.f / 3.f) - bmin.z) * binv.z;
+  uint32_t x = (uint32_t)fminf(fmaxf(cx * 1024.f, 0.f), 1023.f), y = (uint32_t)fminf(fmaxf(cy * 1024.f, 0.f), 1023.f),
+           z = (uint32_t)fminf(fmaxf(cz * 1024.f, 0.f), 1023.f);
+  uint32_t m = (expand_bits10(x) << 2) | (expand_bits10(y) << 1) | expand_bits10(z);
+  keys[f] = ((unsigned long long)m << 32) | (unsigned long long)(uint32_t)f;
 }
 
-#define CB_TILE 1024
-// mode 0: count[cell] = #candidates; mode 1: fill lists (ascending face index)
-__global__ void __launch_bounds__(128) k_cell_lists(GridDesc g, const float4* __restrict__ sphere, int nf, int mode,
-                                                     int32_t* __restrict__ count, const int32_t* __restrict__ start,
-                                                     int32_t* __restrict__ lists) {
-  __shared__ float4 ss[CB_TILE];
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  bool live = c < g.ncell;
-  int cz = c / (g.dims.x * g.dims.y), rem = c - cz * g.dims.x * g.dims.y, cy = rem / g.dims.x, cx = rem - cy * g.dims.x;
-  float qx = g.gmin.x + (cx + 0.5f) * g.cell, qy = g.gmin.y + (cy + 0.5f) * g.cell, qz = g.gmin.z + (cz + 0.5f) * g.cell;
-  const float h = g.cell * 0.8660255f * 1.001f;     // half diagonal
-  // pass A: upper bound U on the distance from the cell centre to the mesh (centroids lie on it)
-  float U = FLT_MAX;
-  for (int base = 0; base < nf; base += CB_TILE) {
-    int cnt = min(CB_TILE, nf - base);
-    __syncthreads();
-    for (int j = threadIdx.x; j < cnt; j += blockDim.x) ss[j] = sphere[base + j];
-    __syncthreads();
-    for (int j = 0; j < cnt; ++j) {
-      float dx = ss[j].x - qx, dy = ss[j].y - qy, dz = ss[j].z - qz;
-      U = fminf(U, dx * dx + dy * dy + dz * dz);
-    }
+__device__ __forceinline__ int bvh_delta(const unsigned long long* __restrict__ k, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  return __clzll(k[i] ^ k[j]);
+}
+
+// Karras 2012: one thread per internal node
+__global__ void k_bvh_hierarchy(const unsigned long long* __restrict__ keys, int n, int2* __restrict__ children,
+                                int32_t* __restrict__ parent, int32_t* __restrict__ leaf_face) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) leaf_face[i] = (int32_t)(keys[i] & 0xffffffffull);
+  if (i >= n - 1) return;
+  int d = (bvh_delta(keys, n, i, i + 1) - bvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = bvh_delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (bvh_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (bvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  int j = i + l * d;
+  int dnode = bvh_delta(keys, n, i, j);
+  int s = 0, t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (bvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  int gamma = i + s * d + min(d, 0);
+  int left = (min(i, j) == gamma) ? (n - 1 + gamma) : gamma;
+  int right = (max(i, j) == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+  children[i] = make_int2(left, right);
+  parent[left] = i;
+  parent[right] = i;
+  if (i == 0) parent[0] = -1;
+}
+
+// bottom-up AABB refit: the second thread to reach a node merges its children
+__global__ void k_bvh_refit(const float* __restrict__ tri9, const int32_t* __restrict__ leaf_face, int n,
+                            const int2* __restrict__ children, const int32_t* __restrict__ parent,
+                            int32_t* __restrict__ visit, float4* lo, float4* hi) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const float* t = tri9 + 9 * (size_t)leaf_face[k];
+  float4 bl = make_float4(fminf(t[0], fminf(t[3], t[6])), fminf(t[1], fminf(t[4], t[7])), fminf(t[2], fminf(t[5], t[8])), 0.f);
+  float4 bh = make_float4(fmaxf(t[0], fmaxf(t[3], t[6])), fmaxf(t[1], fmaxf(t[4], t[7])), fmaxf(t[2], fmaxf(t[5], t[8])), 0.f);
+  int node = n - 1 + k;
+  lo[node] = bl; hi[node] = bh;
+  __threadfence();
+  int cur = (n > 1) ? parent[node] : -1;
+  while (cur >= 0) {
+    if (atomicAdd(&visit[cur], 1) == 0) return;       // first arrival: the sibling subtree is not done yet
+    __threadfence();
+    int2 ch = children[cur];
+    float4 l0 = __ldcg(lo + ch.x), l1 = __ldcg(lo + ch.y), h0 = __ldcg(hi + ch.x), h1 = __ldcg(hi + ch.y);
+    lo[cur] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f);
+    hi[cur] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
+    __threadfence();
+    cur = parent[cur];
   }
-  U = sqrtf(U);
-  const float lim = (U + 2.f * h) * 1.0001f + 1e-6f;
-  // pass B: a triangle can be the closest for some point of the cell only if |q-c|-r <= U + 2h
-  int n = 0;
-  int32_t* out = (mode == 1 && live) ? lists + start[c] : nullptr;
-  for (int base = 0; base < nf; base += CB_TILE) {
-    int cnt = min(CB_TILE, nf - base);
-    __syncthreads();
-    for (int j = threadIdx.x; j < cnt; j += blockDim.x) ss[j] = sphere[base + j];
-    __syncthreads();
-    for (int j = 0; j < cnt; ++j) {
-      float dx = ss[j].x - qx, dy = ss[j].y - qy, dz = ss[j].z - qz;
-      float d = sqrtf(dx * dx + dy * dy + dz * dz) - ss[j].w;
-      if (d <= lim) {
-        if (out) out[n] = base + j;
-        ++n;
-      }
-    }
-  }
-  if (live && mode == 0) count[c] = n;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -127,21 +153,6 @@ __device__ __forceinline__ V3<T> closest_on_tri(V3<T> p, V3<T> a, V3<T> b, V3<T>
   return madd(madd(a, ab, vb * den), ac, vc * den);
 }
 
-__device__ __forceinline__ void test_tri(int f, V3<float> p, const float4* __restrict__ sphere,
-                                         const float* __restrict__ tri9, float& best, int& best_f) {
-  float4 s = __ldg(sphere + f);
-  float dx = s.x - p.x, dy = s.y - p.y, dz = s.z - p.z;
-  float lb = sqrtf(dx * dx + dy * dy + dz * dz) - s.w;
-  if (lb > 0.f && lb * lb > best) return;
-  const float* t = tri9 + 9 * (size_t)f;
-  V3<float> a{__ldg(t), __ldg(t + 1), __ldg(t + 2)}, b{__ldg(t + 3), __ldg(t + 4), __ldg(t + 5)},
-      c{__ldg(t + 6), __ldg(t + 7), __ldg(t + 8)};
-  V3<float> q = closest_on_tri<float>(p, a, b, c);
-  V3<float> e = sub(q, p);
-  float d2 = dot(e, e);
-  if (d2 < best) { best = d2; best_f = f; }
-}
-
 // 4x4 inverse (general, cofactor expansion) in double; returns false if singular
 __host__ __device__ __forceinline__ bool inv4(const double* m, double* o) {
   double s0 = m[0] * m[5] - m[4] * m[1], s1 = m[0] * m[6] - m[4] * m[2], s2 = m[0] * m[7] - m[4] * m[3];
@@ -170,38 +181,79 @@ __host__ __device__ __forceinline__ bool inv4(const double* m, double* o) {
   return true;
 }
 
-__global__ void __launch_bounds__(128) k_warp_points(GridDesc g, const int32_t* __restrict__ cell_start,
-                                                      const int32_t* __restrict__ cell_tris,
-                                                      const float4* __restrict__ sphere, const float* __restrict__ tri9,
-                                                      const float* __restrict__ verts, const int32_t* __restrict__ faces,
-                                                      int nf, const double* __restrict__ T, const float* __restrict__ pts,
-                                                      long long n, double* __restrict__ can64,
-                                                      float* __restrict__ closest_out, int32_t* __restrict__ face_out) {
+__device__ __forceinline__ float box_d2(const BvhView& B, int node, V3<float> p) {
+  const float4 l = __ldg(B.lo + node), h = __ldg(B.hi + node);
+  float dx = fmaxf(fmaxf(l.x - p.x, p.x - h.x), 0.f), dy = fmaxf(fmaxf(l.y - p.y, p.y - h.y), 0.f),
+        dz = fmaxf(fmaxf(l.z - p.z, p.z - h.z), 0.f);
+  return dx * dx + dy * dy + dz * dz;
+}
+
+__global__ void __launch_bounds__(128) k_warp_points(BvhView B, const float* __restrict__ verts,
+                                                      const int32_t* __restrict__ faces, const double* __restrict__ T,
+                                                      const float* __restrict__ pts, long long n,
+                                                      double* __restrict__ can64, float* __restrict__ closest_out,
+                                                      int32_t* __restrict__ face_out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  V3<float> p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+  const bool live = i < n;
+  const long long ii = live ? i : n - 1;
+  V3<float> p{pts[3 * ii], pts[3 * ii + 1], pts[3 * ii + 2]};
   float best = FLT_MAX;
-  int best_f = -1;
-  float fx = (p.x - g.gmin.x) * g.inv_cell, fy = (p.y - g.gmin.y) * g.inv_cell, fz = (p.z - g.gmin.z) * g.inv_cell;
-  bool inside = fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.dims.x && fy < (float)g.dims.y && fz < (float)g.dims.z;
-  if (inside) {
-    int c = ((int)fz * g.dims.y + (int)fy) * g.dims.x + (int)fx;
-    int s = cell_start[c], e = cell_start[c + 1];
-    for (int k = s; k < e; ++k) test_tri(__ldg(cell_tris + k), p, sphere, tri9, best, best_f);
-  } else {
-    for (int f = 0; f < nf; ++f) test_tri(f, p, sphere, tri9, best, best_f);    // exact fallback
+  int best_f = 0x7fffffff;
+  // Exact nearest-triangle search, one BVH traversal per WARP (packet traversal): the 32 lanes hold 32
+  // consecutive samples (neighbours along a ray), a node is visited when ANY lane still needs it (its box is
+  // not farther than that lane's best, 1e-5 slack keeps exact ties alive so the lowest face index wins them),
+  // the nearer child is chosen by majority vote.  Control flow is warp-uniform; only the distances are per lane.
+  __shared__ int s_stack[4][64];
+  int* stack = s_stack[threadIdx.x >> 5];
+  int sp = 0;
+  int node = (B.n > 1) ? 0 : B.n - 1;
+  while (true) {
+    if (node >= B.n - 1) {
+      const int f = __ldg(B.leaf_face + (node - (B.n - 1)));
+      const float* t = B.tri9 + 9 * (size_t)f;
+      V3<float> a{__ldg(t), __ldg(t + 1), __ldg(t + 2)}, b{__ldg(t + 3), __ldg(t + 4), __ldg(t + 5)},
+          c{__ldg(t + 6), __ldg(t + 7), __ldg(t + 8)};
+      V3<float> e = sub(closest_on_tri<float>(p, a, b, c), p);
+      const float d2 = dot(e, e);
+      if (d2 < best || (d2 == best && f < best_f)) { best = d2; best_f = f; }
+      node = -1;
+    } else {
+      const int2 ch = __ldg(B.children + node);
+      const float dl = box_d2(B, ch.x, p), dr = box_d2(B, ch.y, p);
+      const float lim = best * 1.00001f;
+      const bool needL = __any_sync(0xffffffffu, dl <= lim), needR = __any_sync(0xffffffffu, dr <= lim);
+      const bool left_first = __popc(__ballot_sync(0xffffffffu, dl <= dr)) >= 16;
+      if (needL && needR) {
+        if (sp < 64) { if ((threadIdx.x & 31) == 0) stack[sp] = left_first ? ch.y : ch.x; ++sp; }
+        node = left_first ? ch.x : ch.y;
+      } else {
+        node = needL ? ch.x : (needR ? ch.y : -1);
+      }
+    }
+    if (node < 0) {
+      // pop until a node some lane still needs
+      bool found = false;
+      while (sp > 0) {
+        --sp;
+        __syncwarp();
+        const int cand = stack[sp];
+        if (__any_sync(0xffffffffu, box_d2(B, cand, p) <= best * 1.00001f)) { node = cand; found = true; break; }
+      }
+      if (!found) break;
+    }
   }
+  if (!live) return;
   // ---- float64 re-evaluation on the winning triangle (utils/ray_utils.py:53-58) ----
   int i0 = faces[3 * best_f], i1 = faces[3 * best_f + 1], i2 = faces[3 * best_f + 2];
   V3<double> P{(double)p.x, (double)p.y, (double)p.z};
   V3<double> A{(double)verts[3 * i0], (double)verts[3 * i0 + 1], (double)verts[3 * i0 + 2]};
-  V3<double> B{(double)verts[3 * i1], (double)verts[3 * i1 + 1], (double)verts[3 * i1 + 2]};
+  V3<double> Bv{(double)verts[3 * i1], (double)verts[3 * i1 + 1], (double)verts[3 * i1 + 2]};
   V3<double> C{(double)verts[3 * i2], (double)verts[3 * i2 + 1], (double)verts[3 * i2 + 2]};
-  V3<double> Q = closest_on_tri<double>(P, A, B, C);
+  V3<double> Q = closest_on_tri<double>(P, A, Bv, C);
   // barycentric coordinates of Q w.r.t. (A,B,C): signed sub-areas over the area
-  V3<double> nrm = cross(sub(B, A), sub(C, A));
+  V3<double> nrm = cross(sub(Bv, A), sub(C, A));
   double nn = dot(nrm, nrm);
-  double la = dot(nrm, cross(sub(C, B), sub(Q, B))) / nn;
+  double la = dot(nrm, cross(sub(C, Bv), sub(Q, Bv))) / nn;
   double lb = dot(nrm, cross(sub(A, C), sub(Q, C))) / nn;
   double lc = 1.0 - la - lb;
   double M[16], Mi[16];
@@ -247,11 +299,41 @@ static int ensure(nm_ctx* ctx, T** p, size_t* cap, size_t need) {
   return NM_OK;
 }
 
-static GridDesc grid_of(const NmMesh& m) {
-  GridDesc g;
-  g.gmin = m.grid_min; g.cell = m.cell; g.inv_cell = 1.f / m.cell; g.dims = m.dims;
-  g.ncell = m.dims.x * m.dims.y * m.dims.z;
-  return g;
+// one device allocation per mesh holds the whole BVH (+ sort buffers); `cell_start` is its base pointer
+struct BvhLayout {
+  size_t keys_in, keys_out, lo, hi, children, parent, visit, leaf_face, tri9, cub_tmp, total;
+};
+static BvhLayout bvh_layout(int n, size_t cub_bytes) {
+  BvhLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+  L.keys_in = take(sizeof(unsigned long long) * n);
+  L.keys_out = take(sizeof(unsigned long long) * n);
+  L.lo = take(sizeof(float4) * (2 * (size_t)n));
+  L.hi = take(sizeof(float4) * (2 * (size_t)n));
+  L.children = take(sizeof(int2) * (size_t)n);
+  L.parent = take(sizeof(int32_t) * (2 * (size_t)n));
+  L.visit = take(sizeof(int32_t) * (size_t)n);
+  L.leaf_face = take(sizeof(int32_t) * (size_t)n);
+  L.tri9 = take(sizeof(float) * 9 * (size_t)n);
+  L.cub_tmp = take(cub_bytes);
+  L.total = off;
+  return L;
+}
+
+static BvhView bvh_view(const NmMesh& m) {
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, m.n_faces);
+  BvhLayout L = bvh_layout(m.n_faces, cub_bytes);
+  char* base = reinterpret_cast<char*>(m.cell_start);
+  BvhView B;
+  B.n = m.n_faces;
+  B.lo = reinterpret_cast<const float4*>(base + L.lo);
+  B.hi = reinterpret_cast<const float4*>(base + L.hi);
+  B.children = reinterpret_cast<const int2*>(base + L.children);
+  B.leaf_face = reinterpret_cast<const int32_t*>(base + L.leaf_face);
+  B.tri9 = reinterpret_cast<const float*>(base + L.tri9);
+  return B;
 }
 
 extern "C" int nm_mesh_set(nm_ctx* ctx, int actor, const float* verts, int32_t n_verts, const int32_t* faces,
@@ -264,22 +346,13 @@ extern "C" int nm_mesh_set(nm_ctx* ctx, int actor, const float* verts, int32_t n
   int rc;
   if ((rc = ensure(ctx, &m.verts, &m.cap_verts, (size_t)n_verts * 3))) return rc;
   if ((rc = ensure(ctx, &m.T, &m.cap_T, (size_t)n_T * 16))) return rc;
-  {
-    size_t capf = m.cap_faces;
-    if ((rc = ensure(ctx, &m.faces, &capf, (size_t)n_faces * 3))) return rc;
-    if (capf != m.cap_faces || !m.tri_sphere) {
-      // tri_sphere holds [F] float4 followed by the packed triangles [F][9] floats
-      if (m.tri_sphere) { NM_CHECK_CUDA(ctx, cudaFree(m.tri_sphere)); m.tri_sphere = nullptr; }
-      NM_CHECK_CUDA(ctx, cudaMalloc(&m.tri_sphere, capf / 3 * (sizeof(float4) + 9 * sizeof(float)) + 64));
-      m.cap_faces = capf;
-    }
-  }
+  if ((rc = ensure(ctx, &m.faces, &m.cap_faces, (size_t)n_faces * 3))) return rc;
   cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   NM_CHECK_CUDA(ctx, cudaMemcpyAsync(m.verts, verts, (size_t)n_verts * 3 * sizeof(float), kind, st));
   NM_CHECK_CUDA(ctx, cudaMemcpyAsync(m.faces, faces, (size_t)n_faces * 3 * sizeof(int32_t), kind, st));
   NM_CHECK_CUDA(ctx, cudaMemcpyAsync(m.T, T, (size_t)n_T * 16 * sizeof(double), kind, st));
   m.n_verts = n_verts; m.n_faces = n_faces; m.n_T = n_T;
-  // bounding box on the host (82 KB; once per frame)
+  // bounding box on the host (82 KB; once per frame) -- only used to normalise the Morton codes
   std::vector<float> hv((size_t)n_verts * 3);
   if (on_device) {
     NM_CHECK_CUDA(ctx, cudaMemcpyAsync(hv.data(), verts, hv.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -290,34 +363,33 @@ extern "C" int nm_mesh_set(nm_ctx* ctx, int actor, const float* verts, int32_t n
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int v = 0; v < n_verts; ++v)
     for (int c = 0; c < 3; ++c) { lo[c] = fminf(lo[c], hv[3 * v + c]); hi[c] = fmaxf(hi[c], hv[3 * v + c]); }
-  // grid covers the bbox grown by 35% of its longest side (every sample of a geometry-guided ray
-  // lies within geo_threshold of the bbox; points outside take the exact brute-force path)
-  float ext = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
-  float pad = 0.35f * ext;
-  m.cell = (ext + 2 * pad) / GRID_MAX_DIM;
-  m.grid_min = make_float3(lo[0] - pad, lo[1] - pad, lo[2] - pad);
-  m.dims = make_int3(max(1, (int)ceilf((hi[0] - lo[0] + 2 * pad) / m.cell)), max(1, (int)ceilf((hi[1] - lo[1] + 2 * pad) / m.cell)),
-                     max(1, (int)ceilf((hi[2] - lo[2] + 2 * pad) / m.cell)));
-  GridDesc g = grid_of(m);
-  float* tri9 = reinterpret_cast<float*>(m.tri_sphere + n_faces);
-  k_tri_prepare<<<(n_faces + 127) / 128, 128, 0, st>>>(m.verts, m.faces, n_faces, m.tri_sphere, tri9);
+  float3 bmin = make_float3(lo[0], lo[1], lo[2]);
+  float3 binv = make_float3(1.f / fmaxf(hi[0] - lo[0], 1e-20f), 1.f / fmaxf(hi[1] - lo[1], 1e-20f), 1.f / fmaxf(hi[2] - lo[2], 1e-20f));
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, n_faces);
+  BvhLayout L = bvh_layout(n_faces, cub_bytes);
+  {
+    size_t cap = m.cap_cells;                 // capacity of the BVH block, in int32 units
+    if ((rc = ensure(ctx, &m.cell_start, &cap, L.total / sizeof(int32_t) + 1))) return rc;
+    m.cap_cells = cap;
+  }
+  char* base = reinterpret_cast<char*>(m.cell_start);
+  auto* keys_in = reinterpret_cast<unsigned long long*>(base + L.keys_in);
+  auto* keys_out = reinterpret_cast<unsigned long long*>(base + L.keys_out);
+  float* tri9 = reinterpret_cast<float*>(base + L.tri9);
+  k_bvh_keys<<<(n_faces + 127) / 128, 128, 0, st>>>(m.verts, m.faces, n_faces, bmin, binv, tri9, keys_in);
   NM_CHECK_LAUNCH(ctx);
-  if ((rc = ensure(ctx, &m.cell_start, &m.cap_cells, (size_t)2 * (g.ncell + 1)))) return rc;
-  int32_t* counts = m.cell_start + (g.ncell + 1);
-  NM_CHECK_CUDA(ctx, cudaMemsetAsync(counts, 0, (size_t)(g.ncell + 1) * sizeof(int32_t), st));
-  k_cell_lists<<<(g.ncell + 127) / 128, 128, 0, st>>>(g, m.tri_sphere, n_faces, 0, counts, nullptr, nullptr);
-  NM_CHECK_LAUNCH(ctx);
-  size_t tmp_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, m.cell_start, g.ncell + 1, st);
-  char* tmp = nullptr;
-  if ((rc = nm_impl_workspace(ctx, tmp_bytes, &tmp))) return rc;
-  NM_CHECK_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, m.cell_start, g.ncell + 1, st));
+  NM_CHECK_CUDA(ctx, cub::DeviceRadixSort::SortKeys(base + L.cub_tmp, cub_bytes, keys_in, keys_out, n_faces, 0, 64, st));
   NM_LAUNCHED(ctx);
-  NM_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_counter, m.cell_start + g.ncell, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
-  m.n_refs = ctx->h_counter[0];
-  if ((rc = ensure(ctx, &m.cell_tris, &m.cap_refs, (size_t)m.n_refs + 1))) return rc;
-  k_cell_lists<<<(g.ncell + 127) / 128, 128, 0, st>>>(g, m.tri_sphere, n_faces, 1, nullptr, m.cell_start, m.cell_tris);
+  auto* children = reinterpret_cast<int2*>(base + L.children);
+  auto* parent = reinterpret_cast<int32_t*>(base + L.parent);
+  auto* visit = reinterpret_cast<int32_t*>(base + L.visit);
+  auto* leaf_face = reinterpret_cast<int32_t*>(base + L.leaf_face);
+  NM_CHECK_CUDA(ctx, cudaMemsetAsync(visit, 0, sizeof(int32_t) * (size_t)n_faces, st));
+  k_bvh_hierarchy<<<(n_faces + 127) / 128, 128, 0, st>>>(keys_out, n_faces, children, parent, leaf_face);
+  NM_CHECK_LAUNCH(ctx);
+  k_bvh_refit<<<(n_faces + 127) / 128, 128, 0, st>>>(tri9, leaf_face, n_faces, children, parent, visit,
+                                                      reinterpret_cast<float4*>(base + L.lo), reinterpret_cast<float4*>(base + L.hi));
   NM_CHECK_LAUNCH(ctx);
   m.set = true;
   return NM_OK;
@@ -340,10 +412,8 @@ extern "C" int nm_warp_to_canonical(nm_ctx* ctx, int actor, const float* pts, in
     ctx->can64_cap = want;
   }
   double* can64 = ctx->can64;
-  GridDesc g = grid_of(m);
-  const float* tri9 = reinterpret_cast<const float*>(m.tri_sphere + m.n_faces);
-  k_warp_points<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(g, m.cell_start, m.cell_tris, m.tri_sphere, tri9, m.verts,
-                                                               m.faces, m.n_faces, m.T, pts, n, can64, closest, face_id);
+  BvhView B = bvh_view(m);
+  k_warp_points<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, m.verts, m.faces, m.T, pts, n, can64, closest, face_id);
   NM_CHECK_LAUNCH(ctx);
   k_warp_dirs<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(can64, R, S, can_pts, can_dirs);
   NM_CHECK_LAUNCH(ctx);

@@ -311,3 +311,64 @@ def warp_samples_to_canonical(pts, verts, faces, T, actor=0, return_face_id=Fals
     if return_face_id:
         return cp, cd, cl, fid
     return cp, cd, cl
+
+
+# ---------------------------------------------------------------------------------------------
+# SMPL per-vertex transforms (models/smpl.py, data_io/neuman_helper.py:299-330)
+# ---------------------------------------------------------------------------------------------
+class SmplModelDevice:
+    """Device copy of the SMPL arrays the path reads (models/smpl.py:73-107): v_template [V,3],
+    shapedirs [V,3,NB], J_regressor [J,V], weights [V,J], parents [J] (parents[0] = -1)."""
+
+    def __init__(self, v_template, shapedirs, J_regressor, weights, parents, device="cuda"):
+        dev = torch.device(device)
+        self.v_template = _f32(v_template, dev)
+        self.shapedirs = _f32(shapedirs, dev)
+        self.J_regressor = _f32(J_regressor, dev)
+        self.weights = _f32(weights, dev)
+        par = np.asarray(parents.cpu() if isinstance(parents, torch.Tensor) else parents).astype(np.int32).copy()
+        par[0] = -1
+        self._par = (C.c_int32 * len(par))(*par.tolist())
+        self.n_verts, self.n_joints = int(self.v_template.shape[0]), int(len(par))
+        self.n_betas = int(self.shapedirs.shape[-1])
+        self.device = dev
+        m = _lib.NmSmplModel()
+        m.v_template, m.shapedirs = self.v_template.data_ptr(), self.shapedirs.data_ptr()
+        m.J_regressor, m.weights = self.J_regressor.data_ptr(), self.weights.data_ptr()
+        m.parents = self._par
+        m.n_verts, m.n_joints, m.n_betas = self.n_verts, self.n_joints, self.n_betas
+        self.struct = m
+
+
+def smpl_verts_transformations(model, poses, betas, concat_joints=False):
+    """SMPL.verts_transformations (models/smpl.py:109-162) -> (vertices [V(+J),3], T [V(+J),4,4]) float32 CUDA."""
+    ctx = Context.get(model.device.index if model.device.index is not None else torch.cuda.current_device())
+    pose = _f32(poses, model.device).reshape(-1)
+    beta = _f32(betas, model.device).reshape(-1)
+    n = model.n_verts + (model.n_joints if concat_joints else 0)
+    T = torch.empty(n, 4, 4, device=model.device)
+    verts = torch.empty(n, 3, device=model.device)
+    with torch.cuda.device(model.device):
+        ctx.check(ctx.lib.nm_smpl_vertex_transforms(ctx.h, C.byref(model.struct), _p(pose), _p(beta), int(bool(concat_joints)),
+                                                    _p(T), _p(verts), _stream()))
+    return verts, T
+
+
+def smpl_scene_transforms(model, pose, betas, alignment, scale):
+    """data_io/neuman_helper.py:299-330: returns (world_verts [V,3] f32, world_joints [J,3] f32,
+    T_da2scene [V+J,4,4] f64) on the device."""
+    ctx = Context.get(model.device.index if model.device.index is not None else torch.cuda.current_device())
+    p = _f32(pose, model.device).reshape(-1)
+    da = torch.zeros(model.n_joints, 3, device=model.device)
+    da[1, 2], da[2, 2] = 1.0, -1.0                                  # the 'da' pose (:293-297)
+    da = da.reshape(-1).contiguous()
+    b = _f32(betas, model.device).reshape(-1)
+    al = np.ascontiguousarray(np.asarray(alignment, dtype=np.float64).reshape(16))
+    alc = (C.c_double * 16)(*al.tolist())
+    n = model.n_verts + model.n_joints
+    T = torch.empty(n, 4, 4, device=model.device, dtype=torch.float64)
+    world = torch.empty(n, 3, device=model.device)
+    with torch.cuda.device(model.device):
+        ctx.check(ctx.lib.nm_smpl_scene_transforms(ctx.h, C.byref(model.struct), _p(p), _p(da), _p(b), alc, float(scale),
+                                                   _p(T), _p(world), _stream()))
+    return world[:model.n_verts], world[model.n_verts:], T
