@@ -19,7 +19,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __global__ void __launch_bounds__(256) k_raw2outputs(
     const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d, long long R,
-    int S, const float* __restrict__ noise, float sigma_scale, int white_bkg, float* __restrict__ rgb_out,
+    int S, const float* __restrict__ noise, float sigma_scale, int white_bkg, float z_end, float* __restrict__ rgb_out,
     float* __restrict__ disp_out, float* __restrict__ acc_out, float* __restrict__ w_out,
     float* __restrict__ depth_out) {
   const int lane = threadIdx.x & 31;
@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(256) k_raw2outputs(
     if (live) {
       v = rr[s];
       zc = zr[s];
-      float dist = (s + 1 < S) ? (zr[s + 1] - zc) : 1e10f;             // (:85-86)
+      // z_end > 0: zero-density samples follow at z_end (multi-person placeholders, render_utils.py:418-419)
+      float dist = (s + 1 < S) ? (zr[s + 1] - zc) : (z_end > 0.f ? z_end - zc : 1e10f);   // (:85-86)
       dist = dist * dnorm;                                             // (:88)
       float sg = v.w * sigma_scale;
       if (noise) sg = sg + noise[r * S + s];                           // (:91-94)
@@ -81,6 +82,16 @@ __global__ void __launch_bounds__(256) k_raw2outputs(
   }
 }
 
+int nm_impl_raw2outputs_zend(nm_ctx* ctx, const float* raw, const float* z, const float* rays_d, int64_t R, int32_t S,
+                             int32_t white_bkg, float z_end, float* rgb, float* depth, cudaStream_t st) {
+  if (R == 0) return NM_OK;
+  unsigned blocks = (unsigned)((R * 32 + 255) / 256);
+  k_raw2outputs<<<blocks, 256, 0, st>>>((const float4*)raw, z, rays_d, R, S, nullptr, 1.f, white_bkg, z_end, rgb, nullptr,
+                                        nullptr, nullptr, depth);
+  NM_CHECK_LAUNCH(ctx);
+  return NM_OK;
+}
+
 extern "C" int nm_raw2outputs(nm_ctx* ctx, const float* raw, const float* z, const float* rays_d, int64_t R,
                               int32_t S, const float* noise, float sigma_scale, int32_t white_bkg, float* rgb,
                               float* disp, float* acc, float* weights, float* depth, void* stream) {
@@ -89,7 +100,7 @@ extern "C" int nm_raw2outputs(nm_ctx* ctx, const float* raw, const float* z, con
   if (!raw || !z || !rays_d || R < 0 || S <= 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_raw2outputs: bad argument");
   unsigned blocks = (unsigned)((R * 32 + 255) / 256);
   k_raw2outputs<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)raw, z, rays_d, R, S, noise, sigma_scale,
-                                                            white_bkg, rgb, disp, acc, weights, depth);
+                                                            white_bkg, -1.f, rgb, disp, acc, weights, depth);
   NM_CHECK_LAUNCH(ctx);
   return NM_OK;
 }

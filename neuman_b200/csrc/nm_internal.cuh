@@ -110,6 +110,9 @@ __host__ __device__ __forceinline__ float nm_linspace01(int i, int steps) {
 // ---- implemented in the individual .cu files ------------------------------------------------
 int nm_impl_workspace(nm_ctx* ctx, size_t bytes, char** out);
 
+// composite.cu: raw2outputs whose last sample is followed by zero-density samples starting at z_end
+int nm_impl_raw2outputs_zend(nm_ctx* ctx, const float* raw, const float* z, const float* rays_d, int64_t R, int32_t S,
+                             int32_t white_bkg, float z_end, float* rgb, float* depth, cudaStream_t st);
 // mlp_simt.cu
 int nm_simt_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* views,
                     const float* origins, const float* dirs, const float* z, int64_t n,

@@ -78,6 +78,11 @@ __global__ void k_move_rows(const int32_t* __restrict__ idx, long long n, int wi
   else dst[t] = src[r * width + c];
 }
 
+__global__ void k_mark_rows(const int32_t* __restrict__ idx, long long n, float* __restrict__ flag) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) flag[idx[t]] = 1.f;
+}
+
 __global__ void k_fill(float* __restrict__ p, long long n, float v) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) p[t] = v;
@@ -289,7 +294,7 @@ extern "C" int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int
   const int64_t C = std::min<int64_t>(chunk_of(opt), n > 0 ? n : 1);
   ctx->last_mlp_evals = 0; ctx->last_hit_rays = 0;
   size_t per_ray = 6 + 2 + 1 + 8 + 9 * S + (size_t)5 * S + 6 * S + 5 * Sb + 5 * Sb + 5 * Sm + 8 + 5 +
-                   (multi_person ? (size_t)5 * S * n_actors : 0);
+                   (multi_person ? (size_t)10 * S * n_actors + 2 : 0);
   size_t bytes = (size_t)C * per_ray * sizeof(float) + 64 * 256;
   Arena A;
   TRY(nm_impl_workspace(ctx, bytes, &A.base));
@@ -306,8 +311,15 @@ extern "C" int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int
   float* rgb_h = A.take<float>(3 * C); float* dep_h = A.take<float>(C); float* acc_h = A.take<float>(C);
   float* rgb_s = A.take<float>(3 * C); float* dep_s = A.take<float>(C); float* acc_s = A.take<float>(C);
   float* z_a[NM_MAX_ACTORS]; float* raw_a[NM_MAX_ACTORS];
-  if (multi_person)
-    for (int a = 0; a < n_actors; ++a) { z_a[a] = A.take<float>(C * S); raw_a[a] = A.take<float>(4 * C * S); }
+  float* zu_a[NM_MAX_ACTORS]; float* rawu_a[NM_MAX_ACTORS];      // the same rows, compacted to the rays any actor hits
+  float *flag = nullptr, *zeros = nullptr;
+  if (multi_person) {
+    for (int a = 0; a < n_actors; ++a) {
+      z_a[a] = A.take<float>(C * S); raw_a[a] = A.take<float>(4 * C * S);
+      zu_a[a] = A.take<float>(C * S); rawu_a[a] = A.take<float>(4 * C * S);
+    }
+    flag = A.take<float>(C); zeros = A.take<float>(C);
+  }
 
   if (A.off > ctx->ws_bytes) NM_FAIL(ctx, NM_ERR_STATE, "render: workspace arena overflow (internal sizing bug)");
   for (int64_t i = 0; i < n; i += C) {
@@ -345,8 +357,12 @@ extern "C" int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int
         LAUNCH1D(k_move_rows, Rh, st, hit, Rh, 1, acc_h, acc_dst, 1);
       }
     } else {
-      const float* zl[1 + NM_MAX_ACTORS]; const float* rl[1 + NM_MAX_ACTORS]; int32_t Sl[1 + NM_MAX_ACTORS];
-      zl[0] = z_b; rl[0] = raw_b; Sl[0] = St;
+      // Rays no actor hits carry only zero-density placeholders behind the background samples (:418-419): their
+      // composite is the background composite whose last interval ends at the first placeholder (z = 2 far), no
+      // sort needed.  Rays at least one actor hits go through the full z-sorted merge (:441-448), compacted.
+      TRY(nm_impl_raw2outputs_zend(ctx, raw_b, z_b, d, c, St, opt->white_bkg, opt->far_bkg * 2.f, rgb_dst, dep_dst, st));
+      LAUNCH1D(k_fill, c, st, flag, c, 0.f);
+      LAUNCH1D(k_fill, c, st, zeros, c, 0.f);
       for (int a = 0; a < n_actors; ++a) {
         const NmMesh& mesh = ctx->meshes[actors[a]];
         LAUNCH1D(k_fill_placeholder, c * S, st, z_a[a], (float4*)raw_a[a], c, S, opt->far_bkg * 2.f, opt->far_bkg * 3.f);
@@ -359,12 +375,28 @@ extern "C" int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int
           TRY(human_branch(ctx, human_slots[a], actors[a], opt, oh, dh, nh, fh, Rh, pts, cpts, cdirs, z_h, raw_h, false, st));
           LAUNCH1D(k_move_rows, Rh * S, st, hit, Rh, S, z_h, z_a[a], 1);                 // (:438-439)
           LAUNCH1D(k_move_rows, Rh * S * 4, st, hit, Rh, S * 4, raw_h, raw_a[a], 1);
+          LAUNCH1D(k_mark_rows, Rh, st, hit, Rh, flag);
         }
-        zl[1 + a] = z_a[a]; rl[1 + a] = raw_a[a]; Sl[1 + a] = S;
       }
-      TRY(nm_merge_samples(ctx, n_lists, zl, rl, Sl, c, z_m, raw_m, st));                // (:441-448)
-      TRY(nm_raw2outputs(ctx, raw_m, z_m, d, c, Sm, nullptr, 1.f, opt->white_bkg, rgb_dst, nullptr, nullptr, nullptr,
-                         dep_dst, st));                                                // (:449-454)
+      int64_t Ru = 0;
+      TRY(compact(ctx, zeros, flag, c, hit, &Ru, st));                                   // rays with flag > 0
+      if (Ru > 0) {
+        const float* zl[1 + NM_MAX_ACTORS]; const float* rl[1 + NM_MAX_ACTORS]; int32_t Sl[1 + NM_MAX_ACTORS];
+        LAUNCH1D(k_gather_rays, Ru, st, hit, (int)Ru, o, d, zeros, flag, oh, dh, nh, fh);
+        LAUNCH1D(k_move_rows, Ru * St, st, hit, Ru, St, z_b, z_bh, 0);
+        LAUNCH1D(k_move_rows, Ru * St * 4, st, hit, Ru, St * 4, raw_b, raw_bh, 0);
+        zl[0] = z_bh; rl[0] = raw_bh; Sl[0] = St;
+        for (int a = 0; a < n_actors; ++a) {
+          LAUNCH1D(k_move_rows, Ru * S, st, hit, Ru, S, z_a[a], zu_a[a], 0);
+          LAUNCH1D(k_move_rows, Ru * S * 4, st, hit, Ru, S * 4, raw_a[a], rawu_a[a], 0);
+          zl[1 + a] = zu_a[a]; rl[1 + a] = rawu_a[a]; Sl[1 + a] = S;
+        }
+        TRY(nm_merge_samples(ctx, n_lists, zl, rl, Sl, Ru, z_m, raw_m, st));              // (:441-448)
+        TRY(nm_raw2outputs(ctx, raw_m, z_m, dh, Ru, Sm, nullptr, 1.f, opt->white_bkg, rgb_h, nullptr, nullptr, nullptr,
+                           dep_h, st));                                                // (:449-454)
+        LAUNCH1D(k_move_rows, Ru * 3, st, hit, Ru, 3, rgb_h, rgb_dst, 1);
+        LAUNCH1D(k_move_rows, Ru, st, hit, Ru, 1, dep_h, dep_dst, 1);
+      }
       LAUNCH1D(k_fill, c, st, acc_dst, c, 0.f);
     }
     if (host_out) {
