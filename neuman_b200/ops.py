@@ -372,3 +372,17 @@ def smpl_scene_transforms(model, pose, betas, alignment, scale):
         ctx.check(ctx.lib.nm_smpl_scene_transforms(ctx.h, C.byref(model.struct), _p(p), _p(da), _p(b), alc, float(scale),
                                                    _p(T), _p(world), _stream()))
     return world[:model.n_verts], world[model.n_verts:], T
+
+
+def near_far_cache(cap, verts, geo_threshold=DEFAULT_GEO_THRESH, device=None):
+    """The per-frame array `export_near_far_cache` writes (data_io/cache_helper.py:16-36): [H,W,3] float64 =
+    (near, far, 1) of geometry_guided_near_far for every pixel (inf / -inf where the ray misses).  One ray
+    generation + one near/far launch for the whole frame instead of the reference's chunked torch loop."""
+    device = torch.device(device or "cuda")
+    o, d = shot_all_rays(cap, device=device, mode=0)          # shot_rays semantics over all pixels (:28-29)
+    near, far = geometry_guided_near_far(o, d, _f32(verts, device), geo_threshold)
+    H, W = int(cap.shape[0]), int(cap.shape[1])
+    out = np.ones([H, W, 3])
+    out[..., 0] = near.cpu().numpy().reshape(H, W)
+    out[..., 1] = far.cpu().numpy().reshape(H, W)
+    return out

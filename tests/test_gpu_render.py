@@ -102,3 +102,59 @@ def test_full_size_properties(nets):
     rgb = a_rgb[:1024].cpu().numpy()
     assert np.abs(rgb - rgb_o).max() < TOL and np.abs(a_dep[:1024].cpu().numpy() - dep_o).max() < 3 * TOL
     assert abs(round(util.psnr(rgb, 0.5 * np.ones_like(rgb)), 2) - round(util.psnr(rgb_o, 0.5 * np.ones_like(rgb)), 2)) <= 0.01
+
+
+def test_human_shard_chunk_invariance_and_determinism(human):
+    """Hit rays are compacted with atomics (order varies run to run): results must not depend on it, nor on
+    the device chunk size or the pixel range the frame is sharded into."""
+    b1, b2 = util.bodies()
+    H, W = 96, 128
+    K, c2w = scenes.camera(H, W, focal=110.0, seed=0)
+    cap = nb.SimpleCapture(K, c2w, H, W, 0.0, 3.14)
+    geo = b1["geo_threshold"]
+    full = render.render_hybrid_nerf_range(human, cap, b1["verts"], b1["faces"], b1["Ts"], 32, 32, True, geo, host_out=False)
+    again = render.render_hybrid_nerf_range(human, cap, b1["verts"], b1["faces"], b1["Ts"], 32, 32, True, geo, host_out=False)
+    small = render.render_hybrid_nerf_range(human, cap, b1["verts"], b1["faces"], b1["Ts"], 32, 32, True, geo, host_out=False,
+                                            chunk=777)
+    for a, b, c in zip(full, again, small):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    assert 0 < int((full[2] > 0).sum()) < H * W                      # hits and misses both present
+    p0, n = 3000, 5000
+    part = render.render_hybrid_nerf_range(human, cap, b1["verts"], b1["faces"], b1["Ts"], 32, 32, True, geo, pix0=p0, n=n,
+                                           host_out=True)
+    for a, b in zip(full, part):
+        assert torch.equal(a[p0:p0 + n].cpu(), b)
+    # multi-person: shard invariance through the public function (pix0 / n)
+    m_full = nb.render_hybrid_nerf_multi_persons(human, cap, [human, human], [b1["verts"], b2["verts"]], [b1["faces"]] * 2,
+                                                 [b1["Ts"], b2["Ts"]], samples_per_ray=32, importance_samples_per_ray=32,
+                                                 geo_threshold=geo)
+    m_part = nb.render_hybrid_nerf_multi_persons(human, cap, [human, human], [b1["verts"], b2["verts"]], [b1["faces"]] * 2,
+                                                 [b1["Ts"], b2["Ts"]], samples_per_ray=32, importance_samples_per_ray=32,
+                                                 geo_threshold=geo, pix0=p0, n=n)
+    assert np.array_equal(m_full.reshape(-1, 3)[p0:p0 + n], m_part)
+
+
+def test_human_all_miss_frame(human):
+    """Camera looking away from the body: every ray misses -> white / zero maps for render_smpl_nerf, the
+    background composite for the hybrid renderers (acc = 0 everywhere)."""
+    b1, _ = util.bodies()
+    H, W = 24, 32
+    K, c2w = scenes.camera(H, W, focal=40.0, seed=0, yaw=1.5708)      # looks along +x: every ray passes >1 unit from the body
+    # (a camera turned fully away would still "hit": the reference accepts spheres behind the origin, near<far<0)
+    cap = nb.SimpleCapture(K, c2w, H, W, 0.0, 3.14)
+    r, d, a = nb.render_smpl_nerf(human, cap, b1["verts"], b1["faces"], b1["Ts"], samples_per_ray=16,
+                                  geo_threshold=b1["geo_threshold"], return_depth=True, return_mask=True)
+    assert (r == 1.0).all() and (d == 0).all() and (a == 0).all()
+    r0 = nb.render_smpl_nerf(human, cap, b1["verts"], b1["faces"], b1["Ts"], samples_per_ray=16, white_bkg=False,
+                             geo_threshold=b1["geo_threshold"])
+    assert (r0 == 0.0).all()
+    rh, dh, ah = render.render_hybrid_nerf_range(human, cap, b1["verts"], b1["faces"], b1["Ts"], 16, 16, True,
+                                                 b1["geo_threshold"], host_out=True)
+    assert (ah == 0).all()
+    cb, fb = (util.oracle_params(m.to("cpu")) for m in (human.coarse_bkg_net, human.fine_bkg_net))
+    human.to(DEV)
+    hp = util.oracle_params(human.coarse_human_net.to("cpu"))
+    human.to(DEV)
+    ro, do_, _ = no.render_hybrid_nerf(cb, fb, hp, K, c2w, H, W, 0.0, 3.14, b1["verts"], b1["faces"], b1["Ts"],
+                                       samples_per_ray=16, importance_samples_per_ray=16, geo_threshold=b1["geo_threshold"])
+    assert np.abs(rh.numpy() - ro).max() < TOL and np.abs(dh.numpy() - do_).max() < 3 * TOL
