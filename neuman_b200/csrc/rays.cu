@@ -88,9 +88,44 @@ extern "C" int nm_raygen(nm_ctx* ctx, const nm_camera* cam, int mode, int64_t pi
 // list streamed through shared memory in tiles.  6890 vertices x 16 B = 110 KB: four tiles of 2048.
 #define NF_TILE 2048
 #define NF_LANES 4
+// bounding sphere of the vertices (bbox centre, max distance): lets whole warps of rays that pass farther than
+// radius + threshold from it skip the vertex loop -- such a ray cannot touch any vertex sphere, so the result
+// (near=+inf, far=-inf) is exactly what the loop would produce.
+__global__ void __launch_bounds__(256) k_vert_bounds(const float* __restrict__ verts, int nv, float4* __restrict__ out) {
+  __shared__ float red[6][256];
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int v = threadIdx.x; v < nv; v += 256)
+    for (int c = 0; c < 3; ++c) { lo[c] = fminf(lo[c], verts[3 * v + c]); hi[c] = fmaxf(hi[c], verts[3 * v + c]); }
+  for (int c = 0; c < 3; ++c) { red[c][threadIdx.x] = lo[c]; red[3 + c][threadIdx.x] = hi[c]; }
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int c = 0; c < 3; ++c) {
+        red[c][threadIdx.x] = fminf(red[c][threadIdx.x], red[c][threadIdx.x + o]);
+        red[3 + c][threadIdx.x] = fmaxf(red[3 + c][threadIdx.x], red[3 + c][threadIdx.x + o]);
+      }
+    __syncthreads();
+  }
+  const float cx = 0.5f * (red[0][0] + red[3][0]), cy = 0.5f * (red[1][0] + red[4][0]), cz = 0.5f * (red[2][0] + red[5][0]);
+  __syncthreads();
+  float r2 = 0.f;
+  for (int v = threadIdx.x; v < nv; v += 256) {
+    float ax = verts[3 * v] - cx, ay = verts[3 * v + 1] - cy, az = verts[3 * v + 2] - cz;
+    r2 = fmaxf(r2, ax * ax + ay * ay + az * az);
+  }
+  red[0][threadIdx.x] = r2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[0][threadIdx.x] = fmaxf(red[0][threadIdx.x], red[0][threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = make_float4(cx, cy, cz, sqrtf(red[0][0]));
+}
+
 __global__ void __launch_bounds__(256) k_near_far(const float* __restrict__ origins,
                                                    const float* __restrict__ dirs, long long R,
-                                                   const float* __restrict__ verts, int nv, float thr2,
+                                                   const float* __restrict__ verts, int nv, float thr2, float thr,
+                                                   const float4* __restrict__ bounds,
                                                    float* __restrict__ near_out, float* __restrict__ far_out) {
   __shared__ float4 sv[NF_TILE];
   const int sl = threadIdx.x & (NF_LANES - 1);
@@ -102,6 +137,22 @@ __global__ void __launch_bounds__(256) k_near_far(const float* __restrict__ orig
     dx = dirs[3 * r]; dy = dirs[3 * r + 1]; dz = dirs[3 * r + 2];
   }
   float nr = INFINITY, fr = -INFINITY;
+  // conservative cull (0.1 % + 1e-6 slack): distance from the ray's LINE to the bounding-sphere centre
+  bool may_hit = false;
+  if (live) {
+    const float4 b = *bounds;
+    const float cx = b.x - ox, cy = b.y - oy, cz = b.z - oz;
+    const float dn2 = dx * dx + dy * dy + dz * dz;
+    const float t = (cx * dx + cy * dy + cz * dz);
+    const float perp2 = (cx * cx + cy * cy + cz * cz) - t * t / dn2;
+    const float lim = (b.w + thr) * 1.001f + 1e-6f;
+    // the reference's discriminant equals the geometric one only for unit directions: no cull otherwise
+    may_hit = !(perp2 > lim * lim) || fabsf(dn2 - 1.f) > 1e-3f;
+  }
+  if (!__syncthreads_or(may_hit)) {                 // the whole block's rays pass clear of the body
+    if (live && sl == 0) { near_out[r] = nr; far_out[r] = fr; }
+    return;
+  }
   for (int base = 0; base < nv; base += NF_TILE) {
     int cnt = min(NF_TILE, nv - base);
     __syncthreads();
@@ -110,6 +161,7 @@ __global__ void __launch_bounds__(256) k_near_far(const float* __restrict__ orig
       sv[j] = make_float4(v[0], v[1], v[2], 0.f);
     }
     __syncthreads();
+    if (may_hit)
 #pragma unroll 4
     for (int j = sl; j < cnt; j += NF_LANES) {
       float4 v = sv[j];
@@ -142,7 +194,11 @@ extern "C" int nm_near_far(nm_ctx* ctx, const float* origins, const float* dirs,
   // geo_threshold**2 is a python double that torch casts to f32 for the subtraction (:213)
   float thr2 = (float)((double)geo_threshold * (double)geo_threshold);
   unsigned blocks = (unsigned)((R * NF_LANES + 255) / 256);
-  k_near_far<<<blocks, 256, 0, (cudaStream_t)stream>>>(origins, dirs, R, verts, n_verts, thr2, near_out, far_out);
+  float4* bounds = reinterpret_cast<float4*>(ctx->d_counter + 16);       // 16-byte aligned scratch in the ctx
+  k_vert_bounds<<<1, 256, 0, (cudaStream_t)stream>>>(verts, n_verts, bounds);
+  NM_CHECK_LAUNCH(ctx);
+  k_near_far<<<blocks, 256, 0, (cudaStream_t)stream>>>(origins, dirs, R, verts, n_verts, thr2, geo_threshold, bounds,
+                                                         near_out, far_out);
   NM_CHECK_LAUNCH(ctx);
   return NM_OK;
 }

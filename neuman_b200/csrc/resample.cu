@@ -114,7 +114,34 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_importance(
   }
   for (int i = total + lane; i < pow2; i += 32) { keys[i] = INFINITY; idx[i] = i; }
   __syncwarp();
-  if (including_old) nm_warp_bitonic_sort(keys, idx, pow2, lane);             // torch.sort (:152)
+  if (including_old) {                                                         // torch.sort (:152)
+    // Both lists are normally already ascending (z_vals by construction, the inverse-CDF samples because u
+    // ascends): then the sorted union is a rank merge -- rank(old i) = i + #{new < z_i}, rank(new j) = j +
+    // #{old <= z_j} -- instead of a full sort.  Any inversion (1-ulp rounding) falls back to the bitonic network.
+    bool sorted = true;
+    for (int i = lane; i + 1 < S; i += 32) sorted = sorted && (keys[i] <= keys[i + 1]);
+    for (int j = lane; j + 1 < N; j += 32) sorted = sorted && (keys[S + j] <= keys[S + j + 1]);
+    if (__all_sync(FULL, sorted)) {
+      float* merged = reinterpret_cast<float*>(idx);
+      for (int i = lane; i < S; i += 32) {
+        const float v = keys[i];
+        int lo = 0, hi = N;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[S + mid] < v) lo = mid + 1; else hi = mid; }
+        merged[i + lo] = v;
+      }
+      for (int j = lane; j < N; j += 32) {
+        const float v = keys[S + j];
+        int lo = 0, hi = S;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] <= v) lo = mid + 1; else hi = mid; }
+        merged[j + lo] = v;
+      }
+      __syncwarp();
+      for (int i = lane; i < total; i += 32) keys[i] = merged[i];
+      __syncwarp();
+    } else {
+      nm_warp_bitonic_sort(keys, idx, pow2, lane);
+    }
+  }
   float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0;
   if (pts || dirs_out) {
     dx = dirs[3 * r]; dy = dirs[3 * r + 1]; dz = dirs[3 * r + 2];
