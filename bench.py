@@ -169,7 +169,9 @@ def main():
 
     def step_e2e():
         if world == 1:
-            rgb, depth = render.render_vanilla_range(coarse, cap, fine, S, N, pix0=0, n=n_pix, host_out=True)
+            # the reference-signature public call: camera in (host), numpy H x W x 3 / H x W frames out
+            rgb, depth = nb.render_vanilla(coarse, cap, fine_net=fine, samples_per_ray=S, importance_samples_per_ray=N,
+                                           return_depth=True)
             return rgb
         frame = step_device()
         host = frame.cpu() if rank == 0 else None
@@ -231,7 +233,8 @@ def main():
                          "mlp_launches": prof["mlp_launches"], "mlp_ms_per_step": prof["mlp_ms"] / args.steps,
                          "mlp_share_of_step": prof["mlp_ms"] / ms_total},
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": 208, "d2h_bytes_per_step": n_pix * 4 * 4,
-                    "api": "neuman_b200.render.render_vanilla_range(host_out=True) -> pinned host rgb+depth"},
+                    "api": "neuman_b200.render_vanilla(coarse, cap, fine_net=fine, ...) -> numpy rgb [720,1280,3] + depth (reference signature); "
+                           "inputs = the capture's K / camera_to_world (208 B host struct), rays are generated on the device"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -86,3 +86,46 @@ def test_repack_on_weight_update(nets):
     assert torch.allclose(b[:, :3], a[:, :3] + 1.0, atol=1e-5) and torch.equal(a[:, 3], b[:, 3])
     with torch.no_grad():
         net.nerf.rgb_linear.bias.sub_(1.0)
+
+
+def test_c_abi_views_per_ray(nets):
+    """nm_mlp_forward with views_per_ray = S (one direction row per ray, include/neuman_b200.h) equals the
+    per-sample-views call; called straight through ctypes."""
+    import ctypes as C
+    from neuman_b200._lib import Context
+    torch.manual_seed(2)
+    R, S = 40, 24
+    pts = torch.randn(R * S, 3, device=DEV)
+    dirs = torch.nn.functional.normalize(torch.randn(R, 3, device=DEV), dim=-1)
+    ctx = Context.get(0)
+    slot = ops.net_slot(nets[0], ctx)
+    for mode in MODES.values():
+        a = torch.empty(R * S, 4, device=DEV)
+        ctx.check(ctx.lib.nm_mlp_forward(ctx.h, slot, mode, pts.data_ptr(), dirs.data_ptr(), R * S, S, a.data_ptr(),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        b = ops.joiner_forward(nets[0], pts, dirs[:, None, :].expand(-1, S, -1).reshape(-1, 3), mode=mode)
+        assert torch.equal(a, b)
+        # error paths: n not a multiple of views_per_ray, unpacked slot
+        rc = ctx.lib.nm_mlp_forward(ctx.h, slot, mode, pts.data_ptr(), dirs.data_ptr(), R * S - 1, S, a.data_ptr(), None)
+        assert rc == -1 and b"multiple" in ctx.lib.nm_last_error(ctx.h)
+    rc = ctx.lib.nm_mlp_forward(ctx.h, 15, 0, pts.data_ptr(), dirs.data_ptr(), 8, 0, a.data_ptr(), None)
+    assert rc == -4
+
+
+def test_large_weights_stay_finite(nets):
+    """fp16 operands: 3x larger weights (activations grow ~3^8) must not overflow to inf/nan and the error
+    must grow no faster than the oracle's own fp32 noise floor allows (documented in DESIGN.md §3)."""
+    import copy
+    net = copy.deepcopy(nets[0]).to("cpu")
+    with torch.no_grad():
+        for p in net.nerf.pts_linears.parameters():
+            p.mul_(1.6)
+    torch.manual_seed(4)
+    pts, views = torch.randn(4096, 3), torch.nn.functional.normalize(torch.randn(4096, 3), dim=-1)
+    with torch.no_grad():
+        ref = no.net_forward(util.oracle_params(net), pts, views)
+    net.to(DEV)
+    y = ops.joiner_forward(net, pts.to(DEV), views.to(DEV), mode=MODES["tc"]).cpu()
+    assert torch.isfinite(y).all()
+    rel = (y - ref).abs().max() / ref.abs().max()
+    assert rel < 2e-3, rel

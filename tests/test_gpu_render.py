@@ -102,6 +102,11 @@ def test_full_size_properties(nets):
     rgb = a_rgb[:1024].cpu().numpy()
     assert np.abs(rgb - rgb_o).max() < TOL and np.abs(a_dep[:1024].cpu().numpy() - dep_o).max() < 3 * TOL
     assert abs(round(util.psnr(rgb, 0.5 * np.ones_like(rgb)), 2) - round(util.psnr(rgb_o, 0.5 * np.ones_like(rgb)), 2)) <= 0.01
+    # BASELINE configs[1]: the same frame at 64 + 128 samples
+    c_rgb, c_dep = render.render_vanilla_range(nets[0], cap, nets[1], 64, 128, pix0=sub0, n=1024, host_out=True)
+    rgb_o, dep_o = no.render_vanilla(cp, fp, K, c2w, H, W, 0.0, 3.14, samples_per_ray=64, importance_samples_per_ray=128,
+                                     ray_subset=idx)
+    assert np.abs(c_rgb.numpy() - rgb_o).max() < TOL and np.abs(c_dep.numpy() - dep_o).max() < 3 * TOL
 
 
 def test_human_shard_chunk_invariance_and_determinism(human):
