@@ -226,6 +226,7 @@ struct TcParams {
   NmPeSpec pos_pe, dir_pe;
   float* raw;
   long long n_tiles;        // number of (pair-)tiles
+  int cslot;                // index of this net's bias table in c_tc_bias (kConst kernels)
   long long* trace;         // optional debug timeline (tools/tc_trace.py): [cta<2][role<2][event<4][256] clock64 stamps
 };
 
@@ -314,9 +315,19 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return d;
 }
 
-__device__ __forceinline__ void load_bias16(float4 (&b)[4], const float* sbias) {
+// Up to TC_CONST_NETS nets keep their bias table in __constant__ memory: every lane reads the same address, so
+// the constant cache broadcasts it and the loads stay off the shared-memory crossbar (which the UMMA operand
+// fetches and the activation stores already load to >80 %).  Further nets use a bias row staged in smem.
+#define TC_CONST_NETS 5
+__constant__ float c_tc_bias[TC_CONST_NETS * TC_BIAS_FLOATS];
+
+template <bool kConst>
+__device__ __forceinline__ void load_bias16(float4 (&b)[4], const float* sbias, int cidx) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) b[g] = *reinterpret_cast<const float4*>(sbias + 4 * g);
+  for (int g = 0; g < 4; ++g) {
+    if (kConst) b[g] = *reinterpret_cast<const float4*>(&c_tc_bias[cidx + 4 * g]);
+    else b[g] = *reinterpret_cast<const float4*>(sbias + 4 * g);
+  }
 }
 
 // 16 accumulator columns [c0, c0+16) of one row: +bias, (alpha head), ReLU, pack, two swizzled 16-byte stores
@@ -348,23 +359,23 @@ __device__ __forceinline__ void epi_sub16(const uint32_t (&v)[16], const float4 
 // Drains `ncols` accumulator columns of this thread's TMEM lane into the activation block, software
 // pipelined over 16-column sub-chunks: the tcgen05.ld and the bias loads of sub-chunk i+1 are in flight
 // while sub-chunk i is converted and stored.
-template <bool RELU, bool ALPHA>
-__device__ __forceinline__ void epi_step(uint32_t t_lane, int cbase, int ncols, const float* sbias, const float (&aw)[8],
-                                         float (&alpha)[4], uint8_t* act, int row) {
+template <bool RELU, bool ALPHA, bool kConst>
+__device__ __forceinline__ void epi_step(uint32_t t_lane, int cbase, int ncols, const float* sbias, int cbias,
+                                         const float (&aw)[8], float (&alpha)[4], uint8_t* act, int row) {
   uint32_t v0[16], v1[16];
   float4 b0[4], b1[4];
   tmem_ld16(t_lane + cbase, v0);
-  load_bias16(b0, sbias + cbase);
+  load_bias16<kConst>(b0, sbias + cbase, cbias + cbase);
 #pragma unroll 1
   for (int c = cbase; c < cbase + ncols; c += 32) {
     tmem_wait_ld();
     tmem_ld16(t_lane + c + 16, v1);
-    load_bias16(b1, sbias + c + 16);
+    load_bias16<kConst>(b1, sbias + c + 16, cbias + c + 16);
     epi_sub16<RELU, ALPHA>(v0, b0, aw, c, alpha, act, row);
     tmem_wait_ld();
     if (c + 32 < cbase + ncols) {
       tmem_ld16(t_lane + c + 32, v0);
-      load_bias16(b0, sbias + c + 32);
+      load_bias16<kConst>(b0, sbias + c + 32, cbias + c + 32);
     }
     epi_sub16<RELU, ALPHA>(v1, b1, aw, c + 16, alpha, act, row);
   }
@@ -380,7 +391,7 @@ __device__ __forceinline__ void epi_step(uint32_t t_lane, int cbase, int ncols, 
     if (P.trace && blockIdx.x < 2 && (idx) < 256) P.trace[((blockIdx.x * 2 + (role)) * 4 + (ev)) * 256 + (idx)] = clock64(); \
   } while (0)
 
-template <int kPair>
+template <int kPair, bool kConst>
 __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcParams P) {
   using C = TcCfg<kPair>;
   constexpr int NT = C::NT, NSLOT = C::NSLOT;
@@ -563,8 +574,10 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
       for (int j = 0; j < 16; ++j) pe_dir[j] = tmp[j];
     };
     if (n_rounds > 0 && pe_owner) encode_pos(0);
-    sbias[etid] = __ldg(P.bias + etid);            // bias row of step 0
-    epi_barrier();
+    if (!kConst) {
+      sbias[etid] = __ldg(P.bias + etid);          // bias row of step 0
+      epi_barrier();
+    }
 
     for (long long round = 0; round < n_rounds; ++round) {
       // ---- step 0 inputs: positional encoding blocks ----
@@ -579,7 +592,8 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
 #pragma unroll
       for (int t = 0; t < NT; ++t) alpha[t][0] = alpha[t][1] = alpha[t][2] = alpha[t][3] = 0.f;
       for (int s = 0; s < TC_STEPS; ++s, ++nstep) {
-        const float next_bias = (s < 10) ? __ldg(P.bias + ((s + 1) % 10) * TC_BIAS_STRIDE + etid) : 0.f;
+        const float next_bias = (!kConst && s < 10) ? __ldg(P.bias + ((s + 1) % 10) * TC_BIAS_STRIDE + etid) : 0.f;
+        const int cbias = P.cslot * TC_BIAS_FLOATS + s * TC_BIAS_STRIDE;
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           uint8_t* act = smem + C::OFF_ACT + t * 4 * TC_KB_BYTES;
@@ -589,9 +603,9 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
           if (t == 0 && etid == 0) TC_TRACE(1, 0, nstep);
           if (s < 10) {
             const int nh = (s == 9) ? 64 : 128;         // columns drained by this thread
-            if (s == 7) epi_step<true, true>(t_lane, g * nh, nh, sbias, aw, alpha[t], act, row);
-            else if (s == 8) epi_step<false, false>(t_lane, g * nh, nh, sbias, aw, alpha[t], act, row);
-            else epi_step<true, false>(t_lane, g * nh, nh, sbias, aw, alpha[t], act, row);
+            if (s == 7) epi_step<true, true, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row);
+            else if (s == 8) epi_step<false, false, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row);
+            else epi_step<true, false, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row);
             if (s == 7 && g == 1) s_alpha[t * 128 + row] = (alpha[t][0] + alpha[t][1]) + (alpha[t][2] + alpha[t][3]);
             if (s == 4 && g == t) { wait_pe_slot(round, 1, t); store_row_swizzled(pebuf, row, pe_pos, 8); }   // skip input (:131)
             if (s == 8 && g == t) { wait_pe_slot(round, 2, t); store_row_swizzled(pebuf, row, pe_dir, 4); }   // view dirs (:137)
@@ -616,9 +630,11 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
         }
         if (s < 10) {
           // next step's bias row: every epilogue thread is done reading the current one after this barrier
-          epi_barrier();
-          sbias[etid] = next_bias;
-          epi_barrier();
+          if (!kConst) {
+            epi_barrier();
+            sbias[etid] = next_bias;
+            epi_barrier();
+          }
           if (s == 5 && round + 1 < n_rounds && pe_owner) encode_pos(round + 1);
           if (s == 6 && pe_owner) encode_dir(round);
         }
@@ -737,16 +753,22 @@ int nm_tc_pack(nm_ctx* ctx, NmNet& net, cudaStream_t st) {
   k_tc_bias<<<1, 256, 0, st>>>(d.pts_b[0], d.pts_b[1], d.pts_b[2], d.pts_b[3], d.pts_b[4], d.pts_b[5], d.pts_b[6],
                                d.pts_b[7], d.feature_b, d.views_b, d.rgb_b, d.alpha_w, d.alpha_b, net.tc_bias);
   NM_CHECK_LAUNCH(ctx);
+  {
+    const int slot = (int)(&net - ctx->nets);
+    if (slot >= 0 && slot < TC_CONST_NETS)
+      NM_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tc_bias, net.tc_bias, TC_BIAS_FLOATS * sizeof(float),
+                                                 (size_t)slot * TC_BIAS_FLOATS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
 
   return NM_OK;
 }
 
-template <int kPair>
+template <int kPair, bool kConst>
 static int launch_tc(nm_ctx* ctx, const TcParams& P, cudaStream_t st) {
   using C = TcCfg<kPair>;
   static bool attr_set = false;
   if (!attr_set) {
-    NM_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_mlp_tc<kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    NM_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_mlp_tc<kPair, kConst>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   int ctas = ctx->sm_count - (ctx->sm_count % kPair);
@@ -764,7 +786,7 @@ static int launch_tc(nm_ctx* ctx, const TcParams& P, cudaStream_t st) {
   attr[0].val.clusterDim.x = kPair; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NM_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_mlp_tc<kPair>, P));
+  NM_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_mlp_tc<kPair, kConst>, P));
   NM_LAUNCHED(ctx);
   return NM_OK;
 }
@@ -784,5 +806,9 @@ int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* 
   P.n_tiles = (n + 128 * kpair - 1) / (128 * kpair);
   P.trace = nullptr;
   if (const char* e = getenv("NEUMAN_TC_TRACE")) P.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
-  return kpair == 2 ? launch_tc<2>(ctx, P, st) : launch_tc<1>(ctx, P, st);
+  const int slot = (int)(&net - ctx->nets);
+  P.cslot = (slot >= 0 && slot < TC_CONST_NETS) ? slot : 0;
+  if (slot >= 0 && slot < TC_CONST_NETS && getenv("NEUMAN_TC_CONST_BIAS"))   // measured slower than the smem row (1.18 vs 1.45 PFLOP/s): opt-in only
+    return kpair == 2 ? launch_tc<2, true>(ctx, P, st) : launch_tc<1, true>(ctx, P, st);
+  return kpair == 2 ? launch_tc<2, false>(ctx, P, st) : launch_tc<1, false>(ctx, P, st);
 }
