@@ -83,6 +83,26 @@ int nm_net_pack(nm_ctx* ctx, int slot, const nm_nerf_desc* desc, void* stream);
 int nm_mlp_forward(nm_ctx* ctx, int slot, int mode, const float* pts, const float* views,
                    int64_t n, int32_t views_per_ray, float* raw, void* stream);
 
+/* Training forward of the same network (train.py -> trainers/*: Joiner.forward under autograd): as
+ * nm_mlp_forward in NM_MLP_TC_F16 mode, and additionally writes the fp16 activations the backward
+ * pass needs.  stash_x: [8][n][256] post-ReLU outputs of pts_linears 0..7; stash_f: [n][256]
+ * feature_linear output; stash_v: [n][128] views_linears.0 post-ReLU; stash_pe: [n][64] encoded
+ * position (channel 63 zero); stash_dpe: [n][32] encoded direction (channels 27.. zero); stash_m:
+ * [8][n][8] uint32 sign words, bit c of a 256-bit row = [output c of that pts_linears layer > 0]. */
+int nm_mlp_forward_train(nm_ctx* ctx, int slot, const float* pts, const float* views, int64_t n,
+                         int32_t views_per_ray, float* raw, void* stash_x, void* stash_f, void* stash_v,
+                         void* stash_pe, void* stash_dpe, void* stash_m, void* stream);
+
+/* Adjoint of NeRF.forward (models/vanilla.py:120-152) with respect to the layer pre-activations
+ * (what torch autograd computes inside loss.backward() for trainers/vanilla_nerf_trainer.py:222).
+ * d_raw: [n,4] fp32 dL/d(raw); loss_scale: device pointer to one float S (a power of two; all outputs
+ * are S * gradient in fp16).  Outputs: g_pre [8][n][256] = dL/d(pre-activation of pts_linears l),
+ * g_f [n][256] = dL/d(feature), g_v [n][128] = dL/d(pre-activation of views_linears.0).  The weight
+ * gradients are then dW_l = g_l^T @ input_l over the forward stash (GEMMs with K = n, left to the
+ * caller's BLAS), the bias gradients the column sums of g_l. */
+int nm_mlp_backward(nm_ctx* ctx, int slot, const float* d_raw, const float* loss_scale, int64_t n,
+                    const void* stash_v, const void* stash_m, void* g_pre, void* g_f, void* g_v, void* stream);
+
 /* Same network, but the sample positions are generated in-kernel: pts[r,s] = o[r] + d[r]*z[r,s],
  * views = d[r] (utils/ray_utils.py:131-132).  o,d: [R,3]; z: [R,S]; raw: [R,S,4]. */
 int nm_mlp_forward_rays(nm_ctx* ctx, int slot, int mode, const float* origins, const float* dirs,
@@ -132,6 +152,14 @@ int nm_importance_samples(nm_ctx* ctx, const float* origins, const float* dirs, 
 int nm_raw2outputs(nm_ctx* ctx, const float* raw, const float* z, const float* rays_d, int64_t R,
                    int32_t S, const float* noise, float sigma_scale, int32_t white_bkg,
                    float* rgb, float* disp, float* acc, float* weights, float* depth, void* stream);
+
+/* Backward of raw2outputs for training (trainers/vanilla_nerf_trainer.py:64,80): gradients of
+ * rgb_map [R,3], depth_map [R], acc_map [R], weights [R,S] (each may be NULL) -> grad_raw [R,S,4].
+ * disp_map is not differentiated (no caller uses its gradient). */
+int nm_raw2outputs_backward(nm_ctx* ctx, const float* raw, const float* z, const float* rays_d, int64_t R,
+                            int32_t S, const float* noise, float sigma_scale, int32_t white_bkg,
+                            const float* grad_rgb, const float* grad_depth, const float* grad_acc,
+                            const float* grad_weights, float* grad_raw, void* stream);
 
 /* z-sorted merge of several per-ray sample lists + gather of raw (utils/render_utils.py:330-337,
  * :441-448): lists k=0..n_lists-1 with z_k [R,S_k], raw_k [R,S_k,4] -> z_out [R,sum S_k],

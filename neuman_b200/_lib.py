@@ -55,6 +55,8 @@ SIGNATURES = {
     "nm_launch_count": (_I64, [_P]),
     "nm_net_pack": (C.c_int, [_P, C.c_int, C.POINTER(NmNerfDesc), _P]),
     "nm_mlp_forward": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _I64, _I32, _P, _P]),
+    "nm_mlp_forward_train": (C.c_int, [_P, C.c_int, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nm_mlp_backward": (C.c_int, [_P, C.c_int, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "nm_mlp_forward_rays": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _I64, _I32, _P, _P]),
     "nm_raygen": (C.c_int, [_P, C.POINTER(NmCamera), C.c_int, _I64, _I64, _P, _P, _P, _P]),
     "nm_near_far": (C.c_int, [_P, _P, _P, _I64, _P, _I32, _F, _P, _P, _P]),
@@ -62,6 +64,7 @@ SIGNATURES = {
     "nm_sample_pdf": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
     "nm_importance_samples": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P]),
     "nm_raw2outputs": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _F, _I32, _P, _P, _P, _P, _P, _P]),
+    "nm_raw2outputs_backward": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _F, _I32, _P, _P, _P, _P, _P, _P]),
     "nm_merge_samples": (C.c_int, [_P, _I32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I32), _I64, _P, _P, _P]),
     "nm_mesh_set": (C.c_int, [_P, C.c_int, _P, _I32, _P, _I32, _P, _I32, _I32, _P]),
     "nm_warp_to_canonical": (C.c_int, [_P, C.c_int, _P, _I64, _I32, _P, _P, _P, _P, _P]),

@@ -1,0 +1,193 @@
+"""torch.autograd bindings of the hand-written backward kernels (the training-time callers
+trainers/vanilla_nerf_trainer.py:45-96, trainers/human_nerf_trainer.py:382-446).  Forward = the same CUDA
+kernels as inference; backward = their CUDA adjoints.  CUDA tensors only."""
+import ctypes as C
+import os
+
+import torch
+
+from . import ops
+from .ops import _ctx_for, _f32, _p, _stream
+
+
+class _Raw2Outputs(torch.autograd.Function):
+    @staticmethod
+    def forward(fctx, raw, z_vals, rays_d, noise, sigma_scale, white_bkg):
+        r, z, d = _f32(raw), _f32(z_vals, raw.device), _f32(rays_d, raw.device)
+        nz = _f32(noise, raw.device) if noise is not None else None
+        outs = ops.raw2outputs(r, z, d, raw_noise_std=1.0 if nz is not None else 0, white_bkg=white_bkg, noise=nz,
+                               sigma_scale=sigma_scale)
+        fctx.save_for_backward(r, z, d, nz if nz is not None else torch.empty(0, device=r.device))
+        fctx.has_noise = nz is not None
+        fctx.sigma_scale, fctx.white_bkg = float(sigma_scale), bool(white_bkg)
+        fctx.mark_non_differentiable(outs[1])           # disp_map
+        return outs
+
+    @staticmethod
+    def backward(fctx, g_rgb, g_disp, g_acc, g_w, g_depth):
+        r, z, d, nz = fctx.saved_tensors
+        ctx = _ctx_for(r)
+        R, S = z.shape
+        grad_raw = torch.empty_like(r)
+
+        def opt(g):
+            return _f32(g, r.device) if g is not None else None
+        g_rgb, g_acc, g_w, g_depth = opt(g_rgb), opt(g_acc), opt(g_w), opt(g_depth)
+        ctx.check(ctx.lib.nm_raw2outputs_backward(ctx.h, _p(r), _p(z), _p(d), R, S, _p(nz if fctx.has_noise else None),
+                                                  fctx.sigma_scale, int(fctx.white_bkg), _p(g_rgb), _p(g_depth), _p(g_acc),
+                                                  _p(g_w), _p(grad_raw), _stream()))
+        return grad_raw, None, None, None, None, None
+
+
+def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkg=True, noise=None, sigma_scale=1.0):
+    """Differentiable raw2outputs (utils/render_utils.py:69-105): gradients flow to `raw` through rgb_map,
+    acc_map, weights and depth_map."""
+    if raw_noise_std > 0. and noise is None:
+        noise = torch.randn(raw.shape[:-1], device=raw.device) * raw_noise_std
+    return _Raw2Outputs.apply(raw, z_vals, rays_d, noise if raw_noise_std > 0. else None, sigma_scale, white_bkg)
+
+
+# ---------------------------------------------------------------------------------------------
+# Joiner (positional encodings + 8x256 MLP) under autograd
+# ---------------------------------------------------------------------------------------------
+def _pow2_scale(t, target):
+    """0-d fp32 tensor S = 2^k with max|t| * S in [target/2, target]; no host sync."""
+    amax = t.abs().amax().clamp_min(1e-30)
+    return torch.exp2(torch.floor(torch.log2(target / amax))).float().reshape(1)
+
+
+def _mm32(a, b):
+    return torch.mm(a, b, out_dtype=torch.float32)
+
+
+def _use_torch_chain():
+    return os.environ.get("NEUMAN_BWD_TORCH", "0") == "1"
+
+
+class _JoinerMLP(torch.autograd.Function):
+    """forward: k_mlp_tc<.., kTrain> (csrc/mlp_tc.cu) = the inference kernel + an fp16 stash of every layer
+    output, the encodings and the ReLU sign words.
+    backward: k_mlp_tc_bwd (csrc/mlp_tc_bwd.cu) runs the adjoint chain of NeRF.forward (models/vanilla.py:120-152)
+    on the tensor cores and writes S * dL/d(pre-activation) of every layer in fp16 (S = power-of-two loss scale
+    chosen from max|dL/d raw| on the device); the weight gradients are the K = n GEMMs  g_l^T @ input_l  over the
+    stash (cuBLAS through torch.mm, fp16 operands / fp32 accumulate) and the bias gradients column sums.
+    Gradients are produced for the network parameters; sample positions/directions are constants of the step
+    (as in the reference's NeRF trainer, trainers/vanilla_nerf_trainer.py:45-96).
+    NEUMAN_BWD_TORCH=1 evaluates the same chain with torch GEMMs from the same stash (debug / cross-check).
+
+    The gradient is the exact adjoint of the fp16-operand forward: ReLU masks are those of the fp16 activations,
+    so it differs from an fp32 forward's gradient where a pre-activation changes sign under the rounding
+    (DESIGN.md "Training numerics")."""
+
+    @staticmethod
+    def forward(fctx, pts, views, joiner, *params):
+        ctx = _ctx_for(pts)
+        slot = ops.net_slot(joiner, ctx)
+        n = pts.shape[0]
+        dev = pts.device
+        h = dict(device=dev, dtype=torch.float16)
+        sx, sf = torch.empty(8, n, 256, **h), torch.empty(n, 256, **h)
+        sv, spe, sdpe = torch.empty(n, 128, **h), torch.empty(n, 64, **h), torch.empty(n, 32, **h)
+        sm = torch.empty(8, n, 8, device=dev, dtype=torch.int32)
+        raw = torch.empty(n, 4, device=dev, dtype=torch.float32)
+        if n:
+            ctx.check(ctx.lib.nm_mlp_forward_train(ctx.h, slot, _p(pts), _p(views), n, 0, _p(raw), _p(sx), _p(sf), _p(sv),
+                                                   _p(spe), _p(sdpe), _p(sm), _stream()))
+        fctx.joiner = joiner
+        fctx.stash = (sx, sf, sv, spe, sdpe, sm)
+        fctx.save_for_backward(*params)
+        return raw
+
+    @staticmethod
+    def backward(fctx, g_raw):
+        stash = fctx.stash
+        fctx.stash = None
+        nerf = fctx.joiner.nerf
+        names = [k for k, _ in nerf.named_parameters()]
+        P = dict(zip(names, fctx.saved_tensors))
+        g = g_raw.reshape(-1, 4).float().contiguous()
+        if g.shape[0] == 0:
+            grads = {k: torch.zeros_like(v) for k, v in P.items()}
+        elif _use_torch_chain():
+            grads = _chain_torch(fctx.joiner, P, stash, g)
+        else:
+            grads = _chain_kernel(fctx.joiner, P, stash, g)
+        out = [grads[k].reshape(P[k].shape).to(P[k].dtype) if fctx.needs_input_grad[3 + i] else None
+               for i, k in enumerate(names)]
+        return (None, None, None, *out)
+
+
+def _weight_grads(joiner, stash, g, g_pre, g_f, g_v, inv):
+    """dW = g^T @ layer input, db = column sums; g_* are fp16 and carry the loss scale 1/inv."""
+    sx, sf, sv, spe, sdpe, _ = stash
+    n_pe, n_dpe = joiner.pos_pe.out_dim, joiner.dir_pe.out_dim
+    pe, dpe = spe[:, :n_pe], sdpe[:, :n_dpe]
+    grads = {}
+    gh = (g * (1.0 / inv)).half()                                         # [n,4] scaled like the chain outputs
+    grads['rgb_linear.weight'] = _mm32(gh[:, :3].t(), sv) * inv
+    grads['rgb_linear.bias'] = g[:, :3].sum(0)
+    grads['alpha_linear.weight'] = _mm32(gh[:, 3:4].t(), sx[7]) * inv
+    grads['alpha_linear.bias'] = g[:, 3].sum().reshape(1)
+    gvt = g_v.t()
+    grads['views_linears.0.weight'] = torch.cat([_mm32(gvt, sf), _mm32(gvt, dpe)], 1) * inv
+    grads['views_linears.0.bias'] = g_v.sum(0, dtype=torch.float32) * inv
+    grads['feature_linear.weight'] = _mm32(g_f.t(), sx[7]) * inv
+    grads['feature_linear.bias'] = g_f.sum(0, dtype=torch.float32) * inv
+    db = g_pre.sum(1, dtype=torch.float32) * inv                          # [8,256]
+    for l in range(8):
+        gt = g_pre[l].t()
+        if l == 0:
+            w = _mm32(gt, pe)
+        elif l == 5:
+            w = torch.cat([_mm32(gt, pe), _mm32(gt, sx[4])], 1)
+        else:
+            w = _mm32(gt, sx[l - 1])
+        grads['pts_linears.%d.weight' % l] = w * inv
+        grads['pts_linears.%d.bias' % l] = db[l]
+    return grads
+
+
+def _chain_kernel(joiner, P, stash, g):
+    sx, sf, sv, spe, sdpe, sm = stash
+    ctx = _ctx_for(g)
+    slot = ops.net_slot(joiner, ctx)               # same weights as the forward: same slot (or an identical repack)
+    n = g.shape[0]
+    scale = _pow2_scale(g, 256.0)
+    h = dict(device=g.device, dtype=torch.float16)
+    g_pre, g_f, g_v = torch.empty(8, n, 256, **h), torch.empty(n, 256, **h), torch.empty(n, 128, **h)
+    ctx.check(ctx.lib.nm_mlp_backward(ctx.h, slot, _p(g), _p(scale), n, _p(sv), _p(sm), _p(g_pre), _p(g_f), _p(g_v),
+                                      _stream()))
+    return _weight_grads(joiner, stash, g, g_pre, g_f, g_v, 1.0 / scale)
+
+
+def _chain_torch(joiner, P, stash, g):
+    """The chain of k_mlp_tc_bwd restated with torch GEMMs on the same stash (same masks, same fp16 rounding
+    points): the cross-check of the kernel in tests/test_gpu_train.py."""
+    sx, sf, sv, spe, sdpe, sm = stash
+    n_pe = joiner.pos_pe.out_dim
+    scale = _pow2_scale(g, 256.0)
+    inv = 1.0 / scale
+
+    def wh(name):
+        return P[name].detach().half()
+    gs = g * scale
+    g_v = ((gs[:, :3] @ P['rgb_linear.weight'].detach().float()) * (sv > 0)).half()
+    g_f = _mm32(g_v, wh('views_linears.0.weight')[:, :256].contiguous()).half()
+    dX = _mm32(g_f, wh('feature_linear.weight')) + gs[:, 3:4] * P['alpha_linear.weight'].detach().float()
+    g_pre = torch.empty_like(sx)
+    for l in range(7, -1, -1):
+        g_pre[l] = (dX * (sx[l] > 0)).half()
+        if l > 0:
+            w = wh('pts_linears.%d.weight' % l)
+            dX = _mm32(g_pre[l], w[:, n_pe:].contiguous() if l == 5 else w)
+    return _weight_grads(joiner, stash, g, g_pre, g_f, g_v, inv)
+
+
+def joiner_forward(joiner, input_pts, input_views):
+    """Joiner.forward (models/vanilla.py:162-166) with gradients to the network parameters."""
+    shape = input_pts.shape[:-1]
+    pts = _f32(input_pts).reshape(-1, 3)
+    views = _f32(input_views, pts.device).reshape(-1, 3)
+    assert views.shape[0] == pts.shape[0], "input_views must match input_pts"
+    params = [p for _, p in joiner.nerf.named_parameters()]
+    return _JoinerMLP.apply(pts, views, joiner, *params).reshape(*shape, 4)

@@ -29,6 +29,7 @@ static void free_net(NmNet& n) {
   if (n.f32) cudaFree(n.f32);
   if (n.f16) cudaFree(n.f16);
   if (n.tc_bias) cudaFree(n.tc_bias);
+  if (n.f16_bwd) cudaFree(n.f16_bwd);
   n = NmNet();
 }
 
@@ -199,6 +200,7 @@ extern "C" int nm_net_pack(nm_ctx* ctx, int slot, const nm_nerf_desc* d, void* s
     NM_CHECK_CUDA(ctx, cudaMalloc(&n.f32, off * sizeof(float)));
   }
   n.desc = *d;
+  n.bwd_packed = false;
   auto tr = [&](const float* src, size_t dst_off, int n_out, int n_in) {
     int total = n_out * n_in;
     k_transpose<<<(total + 255) / 256, 256, 0, st>>>(src, n.f32 + dst_off, n_out, n_in);
@@ -221,23 +223,33 @@ extern "C" int nm_net_pack(nm_ctx* ctx, int slot, const nm_nerf_desc* d, void* s
   tr(d->rgb_w, n.o_rgb_w, 3, NM_VIEWS_HID);
   NM_CHECK_CUDA(ctx, cp(d->rgb_b, n.o_rgb_b, 3));
   NM_CHECK_CUDA(ctx, cudaGetLastError());
-  std::vector<float> tab;
-  pe_table(d->pos_pe_kind, d->pos_min_freq, d->pos_max_freq, d->pos_n_freqs, tab);
-  NM_CHECK_CUDA(ctx, cudaMemcpyAsync(n.f32 + n.o_pos_bv, tab.data(), tab.size() * sizeof(float),
-                                     cudaMemcpyHostToDevice, st));
-  NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));   // tab is a stack temporary
-  pe_table(d->dir_pe_kind, d->dir_min_freq, d->dir_max_freq, d->dir_n_freqs, tab);
-  NM_CHECK_CUDA(ctx, cudaMemcpyAsync(n.f32 + n.o_dir_bv, tab.data(), tab.size() * sizeof(float),
-                                     cudaMemcpyHostToDevice, st));
-  NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
-  pe_cycles_table(d->pos_pe_kind, d->pos_min_freq, d->pos_max_freq, d->pos_n_freqs, tab);
-  NM_CHECK_CUDA(ctx, cudaMemcpyAsync(n.f32 + n.o_pos_cyc, tab.data(), tab.size() * sizeof(float),
-                                     cudaMemcpyHostToDevice, st));
-  NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
-  pe_cycles_table(d->dir_pe_kind, d->dir_min_freq, d->dir_max_freq, d->dir_n_freqs, tab);
-  NM_CHECK_CUDA(ctx, cudaMemcpyAsync(n.f32 + n.o_dir_cyc, tab.data(), tab.size() * sizeof(float),
-                                     cudaMemcpyHostToDevice, st));
-  NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+  // encoding tables: host-built, uploaded (with a sync, `tab` is a temporary) only when the description changes,
+  // so that re-packing updated weights every training step stays asynchronous
+  const bool same_pe = n.pe_valid && n.pe_desc.pos_pe_kind == d->pos_pe_kind && n.pe_desc.dir_pe_kind == d->dir_pe_kind &&
+                       n.pe_desc.pos_min_freq == d->pos_min_freq && n.pe_desc.pos_max_freq == d->pos_max_freq &&
+                       n.pe_desc.dir_min_freq == d->dir_min_freq && n.pe_desc.dir_max_freq == d->dir_max_freq &&
+                       n.pe_desc.pos_n_freqs == d->pos_n_freqs && n.pe_desc.dir_n_freqs == d->dir_n_freqs;
+  if (!same_pe) {
+    std::vector<float> tab;
+    pe_table(d->pos_pe_kind, d->pos_min_freq, d->pos_max_freq, d->pos_n_freqs, tab);
+    NM_CHECK_CUDA(ctx, cudaMemcpyAsync(n.f32 + n.o_pos_bv, tab.data(), tab.size() * sizeof(float),
+                                       cudaMemcpyHostToDevice, st));
+    NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));   // tab is a stack temporary
+    pe_table(d->dir_pe_kind, d->dir_min_freq, d->dir_max_freq, d->dir_n_freqs, tab);
+    NM_CHECK_CUDA(ctx, cudaMemcpyAsync(n.f32 + n.o_dir_bv, tab.data(), tab.size() * sizeof(float),
+                                       cudaMemcpyHostToDevice, st));
+    NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    pe_cycles_table(d->pos_pe_kind, d->pos_min_freq, d->pos_max_freq, d->pos_n_freqs, tab);
+    NM_CHECK_CUDA(ctx, cudaMemcpyAsync(n.f32 + n.o_pos_cyc, tab.data(), tab.size() * sizeof(float),
+                                       cudaMemcpyHostToDevice, st));
+    NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    pe_cycles_table(d->dir_pe_kind, d->dir_min_freq, d->dir_max_freq, d->dir_n_freqs, tab);
+    NM_CHECK_CUDA(ctx, cudaMemcpyAsync(n.f32 + n.o_dir_cyc, tab.data(), tab.size() * sizeof(float),
+                                       cudaMemcpyHostToDevice, st));
+    NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    n.pe_desc = *d;
+    n.pe_valid = true;
+  }
   int rc = nm_tc_pack(ctx, n, st);
   if (rc != NM_OK) return rc;
   n.packed = true;
@@ -245,7 +257,8 @@ extern "C" int nm_net_pack(nm_ctx* ctx, int slot, const nm_nerf_desc* d, void* s
 }
 
 static int mlp_dispatch(nm_ctx* ctx, int slot, int mode, const float* pts, const float* views, const float* origins,
-                        const float* dirs, const float* z, int64_t n, int32_t group, float* raw, void* stream) {
+                        const float* dirs, const float* z, int64_t n, int32_t group, float* raw, void* stream,
+                        const NmTrainStash* stash = nullptr) {
   if (slot < 0 || slot >= NM_MAX_NET_SLOTS || !ctx->nets[slot].packed)
     NM_FAIL(ctx, NM_ERR_STATE, "nm_mlp_forward: net slot not packed");
   if (n < 0 || !raw) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward: bad argument");
@@ -267,7 +280,7 @@ static int mlp_dispatch(nm_ctx* ctx, int slot, int mode, const float* pts, const
     NM_CHECK_CUDA(ctx, cudaEventRecord(e0, st));
   }
   int rc = mode == NM_MLP_SIMT_F32 ? nm_simt_forward(ctx, net, pts, views, origins, dirs, z, n, group, raw, st)
-                                   : nm_tc_forward(ctx, net, pts, views, origins, dirs, z, n, group, raw, st);
+                                   : nm_tc_forward(ctx, net, pts, views, origins, dirs, z, n, group, raw, st, stash);
   if (ctx->profile && rc == NM_OK) {
     NM_CHECK_CUDA(ctx, cudaEventRecord(e1, st));
     ctx->prof_used += 2;
@@ -283,6 +296,33 @@ extern "C" int nm_mlp_forward(nm_ctx* ctx, int slot, int mode, const float* pts,
   if (views_per_ray > 0 && n % views_per_ray != 0)
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward: n is not a multiple of views_per_ray");
   return mlp_dispatch(ctx, slot, mode, pts, views, nullptr, nullptr, nullptr, n, views_per_ray, raw, stream);
+}
+
+extern "C" int nm_mlp_forward_train(nm_ctx* ctx, int slot, const float* pts, const float* views, int64_t n,
+                                    int32_t views_per_ray, float* raw, void* stash_x, void* stash_f, void* stash_v,
+                                    void* stash_pe, void* stash_dpe, void* stash_m, void* stream) {
+  if (!ctx) return NM_ERR_INVALID;
+  if (!pts || !views || views_per_ray < 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward_train: null pts/views");
+  if (!stash_x || !stash_f || !stash_v || !stash_pe || !stash_dpe || !stash_m)
+    NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward_train: null stash");
+  if (views_per_ray > 0 && n % views_per_ray != 0)
+    NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward_train: n is not a multiple of views_per_ray");
+  NmTrainStash sh{(__half*)stash_x, (__half*)stash_f, (__half*)stash_v, (__half*)stash_pe, (__half*)stash_dpe,
+                  (uint32_t*)stash_m};
+  return mlp_dispatch(ctx, slot, NM_MLP_TC_F16, pts, views, nullptr, nullptr, nullptr, n, views_per_ray, raw, stream, &sh);
+}
+
+extern "C" int nm_mlp_backward(nm_ctx* ctx, int slot, const float* d_raw, const float* loss_scale, int64_t n,
+                               const void* stash_v, const void* stash_m, void* g_pre, void* g_f, void* g_v, void* stream) {
+  if (!ctx) return NM_ERR_INVALID;
+  if (slot < 0 || slot >= NM_MAX_NET_SLOTS || !ctx->nets[slot].packed)
+    NM_FAIL(ctx, NM_ERR_STATE, "nm_mlp_backward: net slot not packed");
+  if (n < 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_backward: bad argument");
+  if (n == 0) return NM_OK;
+  if (!d_raw || !loss_scale || !stash_v || !stash_m || !g_pre || !g_f || !g_v)
+    NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_backward: null argument");
+  return nm_tc_backward(ctx, ctx->nets[slot], d_raw, loss_scale, n, (const __half*)stash_v, (const uint32_t*)stash_m,
+                        (__half*)g_pre, (__half*)g_f, (__half*)g_v, (cudaStream_t)stream);
 }
 
 extern "C" int nm_mlp_forward_rays(nm_ctx* ctx, int slot, int mode, const float* origins, const float* dirs,

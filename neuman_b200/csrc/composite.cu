@@ -177,3 +177,112 @@ extern "C" int nm_merge_samples(nm_ctx* ctx, int32_t n_lists, const float* const
   NM_CHECK_LAUNCH(ctx);
   return NM_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Backward of raw2outputs (utils/render_utils.py:69-105) for training: given the
+// gradients of rgb_map [R,3], depth_map [R], acc_map [R] and weights [R,S] (any may be NULL) returns
+// d raw [R,S,4].  With w_s = alpha_s T_s, T_s = prod_{j<s} (1 - alpha_j + 1e-10):
+//   G_s      = dL/dw_s = sum_c g_rgb_c (c_{s,c} - [white]) + g_depth z_s + g_acc + g_w_s
+//   dL/dalpha_s = G_s T_s - (sum_{k>s} G_k w_k) / (1 - alpha_s + 1e-10)
+//   dL/dsigma_s = dL/dalpha_s * delta_s * exp(-relu(sigma_s) delta_s) * [sigma_s > 0] * sigma_scale
+//   dL/draw_rgb_{s,c} = g_rgb_c w_s c_{s,c} (1 - c_{s,c})
+// (disp_map is not differentiated: the trainers never use its gradient.)  One warp per ray: a forward
+// shuffle scan rebuilds T, a reverse shuffle scan the suffix sums.
+__global__ void __launch_bounds__(256) k_raw2outputs_bwd(
+    const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d, long long R, int S,
+    const float* __restrict__ noise, float sigma_scale, int white_bkg, const float* __restrict__ g_rgb,
+    const float* __restrict__ g_depth, const float* __restrict__ g_acc, const float* __restrict__ g_w,
+    float4* __restrict__ d_raw, float* __restrict__ scratch /* [R,S] G*w */) {
+  const int lane = threadIdx.x & 31;
+  long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= R) return;
+  const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  const float* zr = z + r * S;
+  const float4* rr = raw + r * S;
+  const float gr = g_rgb ? g_rgb[3 * r] : 0.f, gg = g_rgb ? g_rgb[3 * r + 1] : 0.f, gb = g_rgb ? g_rgb[3 * r + 2] : 0.f;
+  const float gd = g_depth ? g_depth[r] : 0.f, ga = g_acc ? g_acc[r] : 0.f;
+  const float wsub = white_bkg ? (gr + gg + gb) : 0.f;
+  // pass 1 (forward): T_s, w_s; store G_s*w_s in scratch, partial results in d_raw
+  float carry = 1.f;
+  for (int base = 0; base < S; base += 32) {
+    int s = base + lane;
+    bool live = s < S;
+    float alpha = 0.f, zc = 0.f, dist = 0.f, sg = 0.f;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (live) {
+      v = rr[s];
+      zc = zr[s];
+      dist = ((s + 1 < S) ? (zr[s + 1] - zc) : 1e10f) * dnorm;
+      sg = v.w * sigma_scale;
+      if (noise) sg = sg + noise[r * S + s];
+      alpha = 1.f - expf(-fmaxf(sg, 0.f) * dist);
+    }
+    float f = live ? (1.f - alpha + 1e-10f) : 1.f;
+    float inc = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float t = __shfl_up_sync(FULL, inc, o);
+      if (lane >= o) inc = inc * t;
+    }
+    float exc = __shfl_up_sync(FULL, inc, 1);
+    if (lane == 0) exc = 1.f;
+    float T = carry * exc;
+    float w = alpha * T;
+    carry = carry * __shfl_sync(FULL, inc, 31);
+    if (live) {
+      float cr = 1.f / (1.f + expf(-v.x)), cg = 1.f / (1.f + expf(-v.y)), cb = 1.f / (1.f + expf(-v.z));
+      float G = gr * cr + gg * cg + gb * cb - wsub + gd * zc + ga + (g_w ? g_w[r * S + s] : 0.f);
+      scratch[r * S + s] = G * w;
+      // x,y,z final; w holds G*T for now (completed in pass 2)
+      d_raw[r * S + s] = make_float4(gr * w * cr * (1.f - cr), gg * w * cg * (1.f - cg), gb * w * cb * (1.f - cb), G * T);
+    }
+  }
+  __syncwarp();
+  // pass 2 (reverse): suffix sums Q_s = sum_{k>s} G_k w_k
+  float tail = 0.f;
+  for (int base = ((S - 1) / 32) * 32; base >= 0; base -= 32) {
+    int s = base + lane;
+    bool live = s < S;
+    float gw = live ? scratch[r * S + s] : 0.f;
+    float inc = gw;                                   // inclusive suffix scan within the chunk
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float t = __shfl_down_sync(FULL, inc, o);
+      if (lane + o < 32) inc += t;
+    }
+    float Q = tail + (inc - gw);                      // exclusive: elements after s
+    tail += __shfl_sync(FULL, inc, 0);
+    if (live) {
+      float4 v = rr[s];
+      float zc = zr[s];
+      float dist = ((s + 1 < S) ? (zr[s + 1] - zc) : 1e10f) * dnorm;
+      float sg = v.w * sigma_scale;
+      if (noise) sg = sg + noise[r * S + s];
+      float e = expf(-fmaxf(sg, 0.f) * dist);
+      float alpha = 1.f - e;
+      float4 o = d_raw[r * S + s];
+      float dalpha = o.w - Q / (1.f - alpha + 1e-10f);
+      o.w = (sg > 0.f) ? dalpha * dist * e * sigma_scale : 0.f;
+      d_raw[r * S + s] = o;
+    }
+  }
+}
+
+extern "C" int nm_raw2outputs_backward(nm_ctx* ctx, const float* raw, const float* z, const float* rays_d, int64_t R,
+                                       int32_t S, const float* noise, float sigma_scale, int32_t white_bkg,
+                                       const float* grad_rgb, const float* grad_depth, const float* grad_acc,
+                                       const float* grad_weights, float* grad_raw, void* stream) {
+  if (!ctx) return NM_ERR_INVALID;
+  if (R == 0) return NM_OK;
+  if (!raw || !z || !rays_d || !grad_raw || R < 0 || S <= 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_raw2outputs_backward: bad argument");
+  char* ws;
+  int rc = nm_impl_workspace(ctx, (size_t)R * S * sizeof(float), &ws);
+  if (rc) return rc;
+  unsigned blocks = (unsigned)((R * 32 + 255) / 256);
+  k_raw2outputs_bwd<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)raw, z, rays_d, R, S, noise, sigma_scale, white_bkg,
+                                                                grad_rgb, grad_depth, grad_acc, grad_weights,
+                                                                (float4*)grad_raw, reinterpret_cast<float*>(ws));
+  NM_CHECK_LAUNCH(ctx);
+  return NM_OK;
+}

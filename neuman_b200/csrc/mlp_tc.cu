@@ -26,162 +26,7 @@
 //               in the epilogue threads' registers and are written to it just before steps 0/5/9).
 #include "nm_internal.cuh"
 #include "nm_pe.cuh"
-
-#define TC_STEPS 11
-#define TC_KB_BYTES 16384          // one A k-block: 128 rows x 128 B
-#define TC_BIAS_STRIDE 256
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-// polling wait with a sleep between probes: for roles that run far ahead of their consumer (the bulk-TMA
-// producer, the relay), so that their spinning does not burn issue slots and power
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns) {
-  uint32_t done = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) break;
-    __nanosleep(ns);
-  }
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// arrive on the barrier at the same offset in CTA `rank` of the cluster (works for rank == self)
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t"
-      ".reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
-      "}" ::"r"(bar), "r"(rank) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-
-template <int kPair>
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  if (kPair == 2)
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  else
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-}
-template <int kPair>
-__device__ __forceinline__ void tmem_relinquish() {
-  if (kPair == 2) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  else asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int kPair>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  if (kPair == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-  else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-
-// D[tmem] (+)= A[smem desc] * B[smem desc], fp16 operands, fp32 accumulate
-template <int kPair>
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
-  if (kPair == 2) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
-  }
-}
-// arrive::one on `bar` (same offset in every CTA of the pair) once all prior MMAs of this thread retire
-template <int kPair>
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  if (kPair == 2) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"((uint16_t)3) : "memory");
-  } else {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-  }
-}
-
-// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=2 [61,64))
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-// UMMA instruction descriptor, kind::f16: D=f32 (bit4), A=B=f16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// {lo, hi} -> packed f16x2 (lo in the low half), optional ReLU
-__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi, bool relu) {
-  uint32_t d;
-  if (relu) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-
+#include "tc_common.cuh"
 // ---------------------------------------------------------------------------------------------
 // Plan: which slabs a step consumes, where they live in the packed image.
 // ---------------------------------------------------------------------------------------------
@@ -227,6 +72,13 @@ struct TcParams {
   float* raw;
   long long n_tiles;        // number of (pair-)tiles
   int cslot;                // index of this net's bias table in c_tc_bias (kConst kernels)
+  // training forward (kTrain): fp16 activation stash for the backward pass, planes of n rows each
+  __half* st_x;             // [8][n][256] post-ReLU outputs of layers 0..7
+  __half* st_f;             // [n][256]    feature_linear output
+  __half* st_v;             // [n][128]    views layer post-ReLU
+  __half* st_pe;            // [n][64]     position encoding (channel 63 = 0)
+  __half* st_dpe;           // [n][32]     direction encoding (channels 27..31 = 0)
+  uint32_t* st_m;           // [8][n][8]   sign words: bit c of row = [layer output c > 0]
   long long* trace;         // optional debug timeline (tools/tc_trace.py): [cta<2][role<2][event<4][256] clock64 stamps
 };
 
@@ -332,8 +184,8 @@ __device__ __forceinline__ void load_bias16(float4 (&b)[4], const float* sbias, 
 
 // 16 accumulator columns [c0, c0+16) of one row: +bias, (alpha head), ReLU, pack, two swizzled 16-byte stores
 template <bool RELU, bool ALPHA>
-__device__ __forceinline__ void epi_sub16(const uint32_t (&v)[16], const float4 (&b)[4], const float (&aw)[8], int c0,
-                                          float (&alpha)[4], uint8_t* act, int row) {
+__device__ __forceinline__ uint32_t epi_sub16(const uint32_t (&v)[16], const float4 (&b)[4], const float (&aw)[8], int c0,
+                                          float (&alpha)[4], uint8_t* act, int row, __half* grow) {
   uint32_t packed[8];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -354,6 +206,17 @@ __device__ __forceinline__ void epi_sub16(const uint32_t (&v)[16], const float4 
   const int ch0 = (c0 & 63) >> 3;
   *reinterpret_cast<uint4*>(blk + ((ch0 ^ (row & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   *reinterpret_cast<uint4*>(blk + (((ch0 + 1) ^ (row & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+  if (grow) {                                   // training: stash the activations for the backward pass
+    *reinterpret_cast<uint4*>(grow + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    *reinterpret_cast<uint4*>(grow + c0 + 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+  }
+  uint32_t bits = 0;                            // bit c-c0 = [output > 0] (used by the training kernel only)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (packed[j] & 0x7fffu) bits |= 1u << (2 * j);
+    if (packed[j] & 0x7fff0000u) bits |= 1u << (2 * j + 1);
+  }
+  return bits;
 }
 
 // Drains `ncols` accumulator columns of this thread's TMEM lane into the activation block, software
@@ -361,7 +224,8 @@ __device__ __forceinline__ void epi_sub16(const uint32_t (&v)[16], const float4 
 // while sub-chunk i is converted and stored.
 template <bool RELU, bool ALPHA, bool kConst>
 __device__ __forceinline__ void epi_step(uint32_t t_lane, int cbase, int ncols, const float* sbias, int cbias,
-                                         const float (&aw)[8], float (&alpha)[4], uint8_t* act, int row) {
+                                         const float (&aw)[8], float (&alpha)[4], uint8_t* act, int row, __half* grow,
+                                         uint4& signs) {
   uint32_t v0[16], v1[16];
   float4 b0[4], b1[4];
   tmem_ld16(t_lane + cbase, v0);
@@ -371,13 +235,16 @@ __device__ __forceinline__ void epi_step(uint32_t t_lane, int cbase, int ncols, 
     tmem_wait_ld();
     tmem_ld16(t_lane + c + 16, v1);
     load_bias16<kConst>(b1, sbias + c + 16, cbias + c + 16);
-    epi_sub16<RELU, ALPHA>(v0, b0, aw, c, alpha, act, row);
+    const uint32_t m0 = epi_sub16<RELU, ALPHA>(v0, b0, aw, c, alpha, act, row, grow);
     tmem_wait_ld();
     if (c + 32 < cbase + ncols) {
       tmem_ld16(t_lane + c + 32, v0);
       load_bias16<kConst>(b0, sbias + c + 32, cbias + c + 32);
     }
-    epi_sub16<RELU, ALPHA>(v1, b1, aw, c + 16, alpha, act, row);
+    const uint32_t m1 = epi_sub16<RELU, ALPHA>(v1, b1, aw, c + 16, alpha, act, row, grow);
+    const uint32_t w = m0 | (m1 << 16);
+    const int q = (c - cbase) >> 5;
+    if (q == 0) signs.x = w; else if (q == 1) signs.y = w; else if (q == 2) signs.z = w; else signs.w = w;
   }
 }
 
@@ -391,7 +258,7 @@ __device__ __forceinline__ void epi_step(uint32_t t_lane, int cbase, int ncols, 
     if (P.trace && blockIdx.x < 2 && (idx) < 256) P.trace[((blockIdx.x * 2 + (role)) * 4 + (ev)) * 256 + (idx)] = clock64(); \
   } while (0)
 
-template <int kPair, bool kConst>
+template <int kPair, bool kConst, bool kTrain>
 __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcParams P) {
   using C = TcCfg<kPair>;
   constexpr int NT = C::NT, NSLOT = C::NSLOT;
@@ -564,6 +431,11 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
       float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
       if (tile_valid(round, g)) nm_fetch_sample(P.in, sample_index(round, g), p, v);
       encode_f16(P.pos_pe, p, pe_pos, 30);
+      if (kTrain && tile_valid(round, g)) {
+        uint4* dst = reinterpret_cast<uint4*>(P.st_pe + (size_t)sample_index(round, g) * 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_uint4(pe_pos[4 * j], pe_pos[4 * j + 1], pe_pos[4 * j + 2], pe_pos[4 * j + 3]);
+      }
     };
     auto encode_dir = [&](long long round) {
       float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
@@ -572,6 +444,11 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
       encode_f16(P.dir_pe, v, tmp, 12);
 #pragma unroll
       for (int j = 0; j < 16; ++j) pe_dir[j] = tmp[j];
+      if (kTrain && tile_valid(round, g)) {
+        uint4* dst = reinterpret_cast<uint4*>(P.st_dpe + (size_t)sample_index(round, g) * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pe_dir[4 * j], pe_dir[4 * j + 1], pe_dir[4 * j + 2], pe_dir[4 * j + 3]);
+      }
     };
     if (n_rounds > 0 && pe_owner) encode_pos(0);
     if (!kConst) {
@@ -603,9 +480,17 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
           if (t == 0 && etid == 0) TC_TRACE(1, 0, nstep);
           if (s < 10) {
             const int nh = (s == 9) ? 64 : 128;         // columns drained by this thread
-            if (s == 7) epi_step<true, true, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row);
-            else if (s == 8) epi_step<false, false, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row);
-            else epi_step<true, false, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row);
+            __half* grow = nullptr;
+            if (kTrain && tile_valid(round, t)) {
+              const long long i = sample_index(round, t);
+              grow = s < 8 ? P.st_x + ((size_t)s * P.in.n + i) * 256 : (s == 8 ? P.st_f + (size_t)i * 256 : P.st_v + (size_t)i * 128);
+            }
+            uint4 signs = make_uint4(0, 0, 0, 0);
+            if (s == 7) epi_step<true, true, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row, grow, signs);
+            else if (s == 8) epi_step<false, false, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row, grow, signs);
+            else epi_step<true, false, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row, grow, signs);
+            if (kTrain && s < 8 && grow)
+              reinterpret_cast<uint4*>(P.st_m + ((size_t)s * P.in.n + sample_index(round, t)) * 8)[g] = signs;
             if (s == 7 && g == 1) s_alpha[t * 128 + row] = (alpha[t][0] + alpha[t][1]) + (alpha[t][2] + alpha[t][3]);
             if (s == 4 && g == t) { wait_pe_slot(round, 1, t); store_row_swizzled(pebuf, row, pe_pos, 8); }   // skip input (:131)
             if (s == 8 && g == t) { wait_pe_slot(round, 2, t); store_row_swizzled(pebuf, row, pe_dir, 4); }   // view dirs (:137)
@@ -763,12 +648,12 @@ int nm_tc_pack(nm_ctx* ctx, NmNet& net, cudaStream_t st) {
   return NM_OK;
 }
 
-template <int kPair, bool kConst>
+template <int kPair, bool kConst, bool kTrain>
 static int launch_tc(nm_ctx* ctx, const TcParams& P, cudaStream_t st) {
   using C = TcCfg<kPair>;
   static bool attr_set = false;
   if (!attr_set) {
-    NM_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_mlp_tc<kPair, kConst>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    NM_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_mlp_tc<kPair, kConst, kTrain>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   int ctas = ctx->sm_count - (ctx->sm_count % kPair);
@@ -786,13 +671,14 @@ static int launch_tc(nm_ctx* ctx, const TcParams& P, cudaStream_t st) {
   attr[0].val.clusterDim.x = kPair; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NM_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_mlp_tc<kPair, kConst>, P));
+  NM_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_mlp_tc<kPair, kConst, kTrain>, P));
   NM_LAUNCHED(ctx);
   return NM_OK;
 }
 
 int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* views, const float* origins,
-                  const float* dirs, const float* z, int64_t n, int32_t group, float* raw, cudaStream_t st) {
+                  const float* dirs, const float* z, int64_t n, int32_t group, float* raw, cudaStream_t st,
+                  const NmTrainStash* stash) {
   const int kpair = tc_pair_mode();
   if (!net.f16 || !net.tc_bias) NM_FAIL(ctx, NM_ERR_STATE, "nm_tc_forward: weights not packed");
   TcParams P;
@@ -805,10 +691,13 @@ int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* 
   P.raw = raw;
   P.n_tiles = (n + 128 * kpair - 1) / (128 * kpair);
   P.trace = nullptr;
+  P.st_x = stash ? stash->x : nullptr; P.st_f = stash ? stash->f : nullptr; P.st_v = stash ? stash->v : nullptr;
+  P.st_pe = stash ? stash->pe : nullptr; P.st_dpe = stash ? stash->dpe : nullptr; P.st_m = stash ? stash->m : nullptr;
   if (const char* e = getenv("NEUMAN_TC_TRACE")) P.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   const int slot = (int)(&net - ctx->nets);
   P.cslot = (slot >= 0 && slot < TC_CONST_NETS) ? slot : 0;
   if (slot >= 0 && slot < TC_CONST_NETS && getenv("NEUMAN_TC_CONST_BIAS"))   // measured slower than the smem row (1.18 vs 1.45 PFLOP/s): opt-in only
-    return kpair == 2 ? launch_tc<2, true>(ctx, P, st) : launch_tc<1, true>(ctx, P, st);
-  return kpair == 2 ? launch_tc<2, false>(ctx, P, st) : launch_tc<1, false>(ctx, P, st);
+    return kpair == 2 ? launch_tc<2, true, false>(ctx, P, st) : launch_tc<1, true, false>(ctx, P, st);
+  if (P.st_x) return kpair == 2 ? launch_tc<2, false, true>(ctx, P, st) : launch_tc<1, false, true>(ctx, P, st);
+  return kpair == 2 ? launch_tc<2, false, false>(ctx, P, st) : launch_tc<1, false, false>(ctx, P, st);
 }

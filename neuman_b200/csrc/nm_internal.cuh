@@ -31,6 +31,10 @@ struct NmNet {
   __half* f16 = nullptr;
   size_t f16_halfs = 0;
   float* tc_bias = nullptr;         // concatenated fp32 biases + alpha weights for the epilogues
+  __half* f16_bwd = nullptr;        // transposed slabs for the backward chain (mlp_tc_bwd.cu), packed on first use
+  bool bwd_packed = false;
+  nm_nerf_desc pe_desc{};           // description the uploaded encoding tables were built from
+  bool pe_valid = false;
 };
 
 struct NmMesh {
@@ -119,7 +123,18 @@ int nm_simt_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float
                     int32_t group, float* raw, cudaStream_t st);
 // mlp_tc.cu
 int nm_tc_pack(nm_ctx* ctx, NmNet& net, cudaStream_t st);
+// fp16 activation stash written by the training forward and read by the backward chain (mlp_tc_bwd.cu)
+struct NmTrainStash {
+  __half* x;     // [8][n][256] post-ReLU outputs of pts_linears 0..7
+  __half* f;     // [n][256]    feature_linear output
+  __half* v;     // [n][128]    views layer post-ReLU
+  __half* pe;    // [n][64]     position encoding
+  __half* dpe;   // [n][32]     direction encoding
+  uint32_t* m;   // [8][n][8]   ReLU sign words of pts_linears 0..7 (bit c of the 256-bit row = [X > 0])
+};
+int nm_tc_backward(nm_ctx* ctx, NmNet& net, const float* d_raw, const float* scale, int64_t n, const __half* st_v,
+                   const uint32_t* st_m, __half* g_pre, __half* g_f, __half* g_v, cudaStream_t st);
 int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* views,
                   const float* origins, const float* dirs, const float* z, int64_t n,
-                  int32_t group, float* raw, cudaStream_t st);
+                  int32_t group, float* raw, cudaStream_t st, const NmTrainStash* stash = nullptr);
 bool nm_tc_available();

@@ -1,7 +1,8 @@
 """Host-side mirror of the reference's network containers (models/vanilla.py:17-250,
 models/human_nerf.py:20-90): same class names, constructor arguments, parameter names and shapes, so
 reference checkpoints (`coarse_model_state_dict`, `hybrid_model_state_dict`, ...) load unchanged.
-`forward()` runs the CUDA path (inference; the hand-written backward is SURVEY.md §8f "next").
+`forward()` runs the CUDA path; under autograd it runs the training kernel (activation stash) and returns
+gradients to the network parameters (neuman_b200/autograd.py).
 """
 import copy
 
@@ -37,7 +38,9 @@ class Embedder(nn.Module):
 
 
 class NeRF(nn.Module):
-    """models/vanilla.py:95-152 (parameter container; same names/shapes)."""
+    """Parameter container with the reference's module names and shapes (models/vanilla.py:95-118):
+    pts_linears.{0..depth-1}, views_linears.0, feature_linear, alpha_linear, rgb_linear (or output_linear).
+    Modules are created in the reference's order so a seeded default init reproduces its weights."""
 
     def __init__(self, depth=8, width=256, input_ch=3, input_ch_views=3, output_ch=4, skips=[4], use_viewdirs=False,
                  scale=1.0, scale_type='no'):
@@ -46,17 +49,20 @@ class NeRF(nn.Module):
         self.input_ch, self.input_ch_views = input_ch, input_ch_views
         self.skips, self.use_viewdirs = skips, use_viewdirs
         self.scale, self.scale_type = scale, scale_type
-        self.pts_linears = nn.ModuleList(
-            [nn.Linear(input_ch, width)] +
-            [nn.Linear(width, width) if i not in self.skips else nn.Linear(width + input_ch, width)
-             for i in range(depth - 1)])
-        if use_viewdirs:
-            self.views_linears = nn.ModuleList([nn.Linear(input_ch_views + width, width // 2)])
-            self.feature_linear = nn.Linear(width, width)
-            self.alpha_linear = nn.Linear(width, 1)
-            self.rgb_linear = nn.Linear(width // 2, 3)
-        else:
+        trunk = []
+        fan_in = input_ch
+        for layer in range(depth):
+            trunk.append(nn.Linear(fan_in, width))
+            # the layer after a skip index sees [encoded input, hidden] (input first, models/vanilla.py:131)
+            fan_in = width + input_ch if layer in self.skips else width
+        self.pts_linears = nn.ModuleList(trunk)
+        if not use_viewdirs:
             self.output_linear = nn.Linear(width, output_ch)
+            return
+        self.views_linears = nn.ModuleList([nn.Linear(width + input_ch_views, width // 2)])
+        self.feature_linear = nn.Linear(width, width)
+        self.alpha_linear = nn.Linear(width, 1)
+        self.rgb_linear = nn.Linear(width // 2, 3)
 
     def forward(self, input_pts, input_views=None):
         raise NotImplementedError("NeRF consumes encoded inputs; the fused CUDA path is Joiner.forward")
@@ -70,7 +76,12 @@ class Joiner(nn.Module):
         self.pos_pe, self.dir_pe, self.nerf = pos_pe, dir_pe, nerf
 
     def forward(self, input_pts, input_views=None):
-        """input_pts [...,3], input_views [...,3] -> [...,4] = (r,g,b,sigma). CUDA only."""
+        """input_pts [...,3], input_views [...,3] -> [...,4] = (r,g,b,sigma). CUDA only.
+        Under autograd (any network parameter requiring grad) the training kernel runs and the result
+        carries gradients to the parameters (neuman_b200/autograd.py)."""
+        if torch.is_grad_enabled() and input_views is not None and any(p.requires_grad for p in self.nerf.parameters()):
+            from . import autograd
+            return autograd.joiner_forward(self, input_pts, input_views)
         return ops.joiner_forward(self, input_pts, input_views)
 
 

@@ -79,9 +79,10 @@ def net_slot(joiner, ctx=None):
     keep = []
 
     def dev(t):
-        t = t.detach().contiguous().float()
-        keep.append(t)
-        return t.data_ptr()
+        c = t.detach().contiguous().float()
+        if c.data_ptr() != t.data_ptr():
+            keep.append(c)                          # a converted temporary: must outlive the pack kernels
+        return c.data_ptr()
     for i in range(8):
         d.pts_w[i] = dev(nerf.pts_linears[i].weight)
         d.pts_b[i] = dev(nerf.pts_linears[i].bias)
@@ -94,7 +95,8 @@ def net_slot(joiner, ctx=None):
     d.pos_min_freq, d.pos_max_freq, d.pos_n_freqs = float(pp.min_freq), float(pp.max_freq), int(pp.N_freqs)
     d.dir_min_freq, d.dir_max_freq, d.dir_n_freqs = float(dp.min_freq), float(dp.max_freq), int(dp.N_freqs)
     ctx.check(ctx.lib.nm_net_pack(ctx.h, s, C.byref(d), _stream()))
-    torch.cuda.current_stream().synchronize()      # `keep` temporaries may be freed after this
+    if keep:
+        torch.cuda.current_stream().synchronize()  # `keep` temporaries may be freed after this
     ctx.slots[key] = s
     ctx.slot_keys[s] = key
     ctx.slot_clock += 1

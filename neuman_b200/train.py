@@ -1,0 +1,84 @@
+"""Training step of the background NeRF on the CUDA path: host mirror of
+trainers/vanilla_nerf_trainer.py:45-96 (`loss_func`) and :206-223 (`train_batch`).
+
+Forward = the inference kernels (ray_to_samples, Joiner training kernel, raw2outputs, inverse-CDF
+resampling); backward = raw2outputs adjoint kernel + the MLP adjoint chain (neuman_b200/autograd.py).
+Sample positions are constants of the step exactly as in the reference (`z_samples.detach()`,
+utils/ray_utils.py:186-192), so no gradient crosses the samplers.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import autograd, ops
+
+
+def vanilla_loss_func(coarse_net, fine_net, batch, opt, penalize_empty_space=0., empty_space_loss_fn=F.l1_loss,
+                      t_rand=None, noise=None, check_bad_weights=True):
+    """trainers/vanilla_nerf_trainer.py:45-96.  batch: origin/direction [R,3], near/far [R], color [R,3]
+    (and depth [R] when penalize_empty_space > 0).  Returns the reference's four losses.
+    `t_rand` / `noise` = (coarse, fine) pairs let a test fix the stratified jitter and the density noise.
+    `check_bad_weights` keeps the reference's dead-density re-initialisation (:84-89); it costs one host
+    sync per step, pass False to run the step fully asynchronously."""
+    if getattr(opt, 'ablate_nerft', False):
+        raise NotImplementedError("ablate_nerft is not on the built path")
+    dev = next(coarse_net.parameters()).device
+    perturb = getattr(opt, 'perturb', 0.)
+    noise_std = getattr(opt, 'raw_noise_std', 0.)
+    color = batch['color'].to(dev)
+    pts, dirs, z_vals = ops.ray_to_samples(batch, opt.samples_per_ray, perturb=perturb, device=dev,
+                                           t_rand=t_rand)
+    _b, _n = z_vals.shape
+    out = coarse_net(pts, dirs)
+    rgb_map, _, _, weights, _ = autograd.raw2outputs(out, z_vals, dirs[:, 0, :], raw_noise_std=noise_std,
+                                                     white_bkg=opt.white_bkg, noise=None if noise is None else noise[0])
+    coarse_rgb_loss = F.mse_loss(rgb_map, color)
+    coarse_empty = torch.zeros_like(coarse_rgb_loss)
+    if penalize_empty_space > 0:
+        depth = batch['depth'].to(dev)[:, None].repeat(1, _n)
+        m = z_vals < (depth * opt.margin)
+        s = out[m][:, 3]
+        coarse_empty = coarse_empty + empty_space_loss_fn(torch.tanh(torch.relu(s)), torch.zeros_like(s)) * penalize_empty_space
+    fine_rgb_loss, fine_empty, F_out = torch.zeros_like(coarse_rgb_loss), torch.zeros_like(coarse_rgb_loss), None
+    if fine_net is not None:
+        F_pts, F_dirs, F_z = ops.ray_to_importance_samples(batch, z_vals, weights.detach(),
+                                                           opt.importance_samples_per_ray, device=dev)
+        F_out = fine_net(F_pts, F_dirs)
+        F_rgb, _, _, _, _ = autograd.raw2outputs(F_out, F_z, F_dirs[:, 0, :], raw_noise_std=noise_std,
+                                                 white_bkg=opt.white_bkg, noise=None if noise is None else noise[1])
+        fine_rgb_loss = F.mse_loss(F_rgb, color)
+        if penalize_empty_space > 0:
+            F_depth = batch['depth'].to(dev)[:, None].repeat(1, F_z.shape[1])
+            m = F_z < (F_depth * opt.margin)
+            s = F_out[m][:, 3]
+            fine_empty = fine_empty + empty_space_loss_fn(torch.tanh(torch.relu(s)), torch.zeros_like(s)) * penalize_empty_space
+    if check_bad_weights:
+        dead = out.detach()[..., 3].max() <= 0.0
+        if F_out is not None:
+            dead = dead | (F_out.detach()[..., 3].max() <= 0.0)
+        if bool(dead):
+            print('bad weights, reinitializing')
+            coarse_net.apply(weight_reset)
+            if fine_net is not None:
+                fine_net.apply(weight_reset)
+            zero = torch.tensor(0.0, requires_grad=True).float().to(dev)
+            return zero, zero, zero, zero
+    return coarse_rgb_loss, coarse_empty, fine_rgb_loss, fine_empty
+
+
+def weight_reset(m):
+    """models/vanilla.py:11-13."""
+    if isinstance(m, torch.nn.Linear):
+        m.reset_parameters()
+
+
+def train_batch(coarse_net, fine_net, optimizer, batch, opt, iteration=0, **kw):
+    """trainers/vanilla_nerf_trainer.py:206-223.  Returns the total loss as a 0-d tensor (no host sync
+    unless the caller reads it)."""
+    optimizer.zero_grad()
+    c_rgb, c_emp, f_rgb, f_emp = vanilla_loss_func(coarse_net, fine_net, batch, opt, **kw)
+    total = c_rgb + f_rgb
+    if iteration >= getattr(opt, 'delay_iters', 0):
+        total = total + c_emp + f_emp
+    total.backward()
+    optimizer.step()
+    return total.detach()

@@ -1,0 +1,195 @@
+"""GPU parity of the backward kernels (training path) against torch autograd of the oracle
+restatement (float32 / float64 on the CPU)."""
+import numpy as np
+import pytest
+import torch
+
+from neuman_b200 import autograd as nag
+from oracle import neuman_oracle as no
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("R,S,white", [(5, 7, True), (64, 128, True), (33, 256, False), (3, 33, True)])
+def test_raw2outputs_backward(R, S, white):
+    torch.manual_seed(R * S)
+    raw = (torch.randn(R, S, 4) * 1.5).double().requires_grad_(True)
+    z = torch.sort(torch.rand(R, S) * 3, -1)[0].double()
+    d = torch.randn(R, 3).double()
+    noise = (torch.randn(R, S) * 0.3).double()
+    # oracle in float64 for a clean reference gradient
+    with torch.enable_grad():
+        dz = torch.cat([z[..., 1:] - z[..., :-1], torch.full_like(z[..., :1], 1e10)], -1) * torch.linalg.norm(d[..., None, :], dim=-1)
+        rgb = torch.sigmoid(raw[..., :3])
+        alpha = 1. - torch.exp(-torch.relu(raw[..., 3] + noise) * dz)
+        T = torch.cumprod(torch.cat([torch.ones(R, 1, dtype=torch.float64), 1. - alpha + 1e-10], -1), -1)[:, :-1]
+        w = alpha * T
+        rgb_map = (w[..., None] * rgb).sum(-2)
+        depth, acc = (w * z).sum(-1), w.sum(-1)
+        if white:
+            rgb_map = rgb_map + (1. - acc[..., None])
+        g_rgb, g_depth, g_acc, g_w = torch.randn(R, 3).double(), torch.randn(R).double(), torch.randn(R).double(), torch.randn(R, S).double()
+        loss = (rgb_map * g_rgb).sum() + (depth * g_depth).sum() + (acc * g_acc).sum() + (w * g_w).sum()
+        loss.backward()
+    ref = raw.grad.float()
+    raw_c = raw.detach().float().to(DEV).requires_grad_(True)
+    outs = nag.raw2outputs(raw_c, z.float().to(DEV), d.float().to(DEV), raw_noise_std=1.0, white_bkg=white, noise=noise.float().to(DEV))
+    l2 = (outs[0] * g_rgb.float().to(DEV)).sum() + (outs[4] * g_depth.float().to(DEV)).sum() + \
+        (outs[2] * g_acc.float().to(DEV)).sum() + (outs[3] * g_w.float().to(DEV)).sum()
+    l2.backward()
+    got = raw_c.grad.cpu()
+    scale = ref.abs().max()
+    assert (got - ref).abs().max() < 2e-5 * max(1.0, float(scale)), ((got - ref).abs().max(), scale)
+    # only rgb gradient (the vanilla trainer's case): other grads None
+    raw_c.grad = None
+    outs = nag.raw2outputs(raw_c, z.float().to(DEV), d.float().to(DEV), white_bkg=white)
+    outs[0].sum().backward()
+    assert torch.isfinite(raw_c.grad).all()
+
+
+def _rel(a, b):
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+class _Q16(torch.autograd.Function):
+    """round to fp16 in the forward, identity in the backward"""
+    @staticmethod
+    def forward(ctx, x):
+        return x.half().float()
+
+    @staticmethod
+    def backward(ctx, gy):
+        return gy
+
+
+def _reference_grads(joiner, pts, views, g, quant):
+    """fp32 CPU autograd of the oracle MLP.  quant=True rounds the GEMM operands (weights, encodings, layer
+    outputs) to fp16 like the tensor-core path, so its ReLU masks are those of the CUDA forward."""
+    import torch.nn.functional as F
+    from tests.util import oracle_params
+    net = oracle_params(joiner)
+    for k in net.sd:
+        net.sd[k].requires_grad_(True)
+    if not quant:
+        raw = no.net_forward(net, pts, views)
+    else:
+        q = _Q16.apply
+        pe, ve = q(no.embed(pts, net.pos_pe)), q(no.embed(views, net.dir_pe))
+        h = pe
+        for i in range(8):
+            pre = F.relu(F.linear(h, q(net.w(f"pts_linears.{i}.weight")), net.w(f"pts_linears.{i}.bias")))
+            if i == 7:
+                alpha = F.linear(pre, net.w("alpha_linear.weight"), net.w("alpha_linear.bias"))   # fp32 head
+            h = q(pre)
+            if i == 4:
+                h = torch.cat([pe, h], -1)
+        feat = q(F.linear(h, q(net.w("feature_linear.weight")), net.w("feature_linear.bias")))
+        hv = q(F.relu(F.linear(torch.cat([feat, ve], -1), q(net.w("views_linears.0.weight")), net.w("views_linears.0.bias"))))
+        raw = torch.cat([F.linear(hv, q(net.w("rgb_linear.weight")), net.w("rgb_linear.bias")), alpha], -1)
+    (raw * g).sum().backward()
+    return raw.detach(), {k[len('nerf.'):]: v.grad for k, v in net.sd.items()}
+
+
+@pytest.mark.parametrize("kind,n", [("posenc", 1000), ("rotate", 4096 + 77), ("posenc", 256 * 148 * 2 + 300)])
+def test_joiner_backward(kind, n, monkeypatch):
+    """Parameter gradients of Joiner.forward.
+    (1) tensor-core backward kernel vs the same chain in torch GEMMs on the same stash: 2e-3 relative L2
+        (fp16 rounding of intermediate gradients at the same points, different accumulation order);
+    (2) vs fp32 CPU autograd of an fp16-operand emulation of the forward (same ReLU masks up to rare
+        accumulation-order flips): 3e-2;
+    (3) vs fp32 CPU autograd of the plain fp32 oracle: 8e-2 -- the fp16 operand rounding flips the sign of
+        ~5e-4 of the pre-activations, and each flip changes that unit's gradient entirely (DESIGN.md
+        "Training numerics"; an fp32-vs-emulation comparison on the CPU alone shows the same 2-3.5 %)."""
+    from tests.util import product_nets
+    coarse, fine, human = product_nets(DEV)
+    j = coarse if kind == "posenc" else human
+    torch.manual_seed(n)
+    pts = torch.randn(n, 3) * 1.5
+    views = torch.nn.functional.normalize(torch.randn(n, 3), dim=-1)
+    g = torch.randn(n, 4)
+
+    def product(torch_chain):
+        monkeypatch.setenv("NEUMAN_BWD_TORCH", "1" if torch_chain else "0")
+        j.zero_grad()
+        raw = j(pts.to(DEV), views.to(DEV))
+        assert raw.requires_grad
+        (raw * g.to(DEV)).sum().backward()
+        return raw.detach().cpu(), {k: p.grad.detach().cpu().clone() for k, p in j.nerf.named_parameters()}
+    raw, got = product(False)
+    _, chain = product(True)
+    for k in got:
+        assert torch.isfinite(got[k]).all(), k
+        assert _rel(got[k], chain[k]) < 2e-3, ("kernel vs torch chain", k, _rel(got[k], chain[k]))
+    if n <= 5000:
+        raw_q, ref_q = _reference_grads(j, pts, views, g, True)
+        raw_f, ref_f = _reference_grads(j, pts, views, g, False)
+        assert (raw - raw_f).abs().max() < 5e-3
+        for k in got:
+            assert got[k].shape == ref_f[k].shape, k
+            assert _rel(got[k], ref_q[k]) < 3e-2, ("vs fp16-operand emulation", k, _rel(got[k], ref_q[k]))
+            assert _rel(got[k], ref_f[k]) < 8e-2, ("vs fp32", k, _rel(got[k], ref_f[k]))
+    # inference path unchanged by the training kernel: same raw under no_grad
+    with torch.no_grad():
+        raw2 = j(pts.to(DEV), views.to(DEV))
+    assert not raw2.requires_grad and torch.equal(raw2.cpu(), raw)
+
+
+def test_vanilla_train_step_matches_autograd():
+    """One loss_func evaluation (trainers/vanilla_nerf_trainer.py:45-96) on the CUDA path vs the oracle's
+    torch restatement under CPU autograd, sharing the stratified jitter, the density noise and the fine
+    sample depths.  Then three optimizer steps on each side: losses stay together."""
+    import copy
+    import neuman_b200 as nb
+    from neuman_b200 import train as nt
+    from tests.util import product_nets, oracle_params
+    import torch.nn.functional as F
+    coarse, fine, _ = product_nets(DEV)
+    coarse, fine = copy.deepcopy(coarse), copy.deepcopy(fine)
+    opt = nb.default_opt(samples_per_ray=32, importance_samples_per_ray=32, perturb=1.0, raw_noise_std=1.0, margin=0.9)
+    R = 300
+    torch.manual_seed(5)
+    o = torch.randn(R, 3) * 0.1
+    d = torch.nn.functional.normalize(torch.randn(R, 3), dim=-1) * (1 + 0.2 * torch.rand(R, 1))
+    batch = dict(origin=o.to(DEV), direction=d.to(DEV), near=torch.full((R,), 0.5, device=DEV),
+                 far=torch.full((R,), 4.0, device=DEV), color=torch.rand(R, 3, device=DEV),
+                 depth=(1.5 + torch.rand(R)).to(DEV))
+    t_rand = torch.rand(R, 32)
+    noise = (torch.randn(R, 32), torch.randn(R, 64))
+    kw = dict(check_bad_weights=False, penalize_empty_space=0.1, t_rand=t_rand.to(DEV), noise=tuple(x.to(DEV) for x in noise))
+    losses = nt.vanilla_loss_func(coarse, fine, batch, opt, **kw)
+    sum(losses).backward()
+    # reference on the CPU with the product's sample depths
+    with torch.no_grad():
+        _, _, z = nb.ray_to_samples(batch, 32, perturb=1.0, t_rand=t_rand.to(DEV))
+        raw_c = coarse(*nb.ray_to_samples(batch, 32, perturb=1.0, t_rand=t_rand.to(DEV))[:2])
+        w = nb.raw2outputs(raw_c, z, batch['direction'], raw_noise_std=1.0, white_bkg=True, noise=noise[0].to(DEV))[3]
+        _, _, Fz = nb.ray_to_importance_samples(batch, z, w, 32)
+    z, Fz = z.cpu(), Fz.cpu()
+    nets = [oracle_params(coarse), oracle_params(fine)]
+    for net in nets:
+        for k in net.sd:
+            net.sd[k].requires_grad_(True)
+
+    def side(net, zz, nz):
+        pts = o[:, None, :] + d[:, None, :] * zz[..., None]
+        raw = no.net_forward(net, pts, d[:, None, :].expand_as(pts))
+        rgb = no.raw2outputs(raw, zz, d, raw_noise_std=1.0, white_bkg=True, noise=nz)[0]
+        m = zz < (batch['depth'].cpu()[:, None] * 0.9)
+        s = raw[m][:, 3]
+        return F.mse_loss(rgb, batch['color'].cpu()), F.l1_loss(torch.tanh(torch.relu(s)), torch.zeros_like(s)) * 0.1
+    ref = side(nets[0], z, noise[0]) + side(nets[1], Fz, noise[1])
+    sum(ref).backward()
+    for a, b in zip(losses, (ref[0], ref[1], ref[2], ref[3])):
+        assert abs(float(a) - float(b)) < 2e-4 * max(1.0, abs(float(b))), (float(a), float(b))
+    for jn, net in zip((coarse, fine), nets):
+        for name, p in jn.nerf.named_parameters():
+            refg = net.sd['nerf.' + name].grad
+            assert _rel(p.grad.cpu(), refg) < 8e-2, (name, _rel(p.grad.cpu(), refg))
+    # a few optimizer steps: the loss goes down and the parameters stay finite
+    optim = torch.optim.Adam(list(coarse.parameters()) + list(fine.parameters()), lr=5e-4)
+    first = last = None
+    for it in range(6):
+        last = float(nt.train_batch(coarse, fine, optim, batch, opt, iteration=it, **kw))
+        first = last if first is None else first
+    assert np.isfinite(last) and last < first, (first, last)
