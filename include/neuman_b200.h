@@ -87,7 +87,8 @@ int nm_mlp_forward(nm_ctx* ctx, int slot, int mode, const float* pts, const floa
  * nm_mlp_forward in NM_MLP_TC_F16 mode, and additionally writes the fp16 activations the backward
  * pass needs.  stash_x: [8][n][256] post-ReLU outputs of pts_linears 0..7; stash_f: [n][256]
  * feature_linear output; stash_v: [n][128] views_linears.0 post-ReLU; stash_pe: [n][64] encoded
- * position (channel 63 zero); stash_dpe: [n][32] encoded direction (channels 27.. zero); stash_m:
+ * position (channel 63 = 1.0); stash_dpe: [n][32] encoded direction (channel 27 = 1.0, 28.. zero): the
+ * constant channel makes g^T @ stash deliver the bias gradient next to the weight gradient; stash_m:
  * [8][n][8] uint32 sign words, bit c of a 256-bit row = [output c of that pts_linears layer > 0]. */
 int nm_mlp_forward_train(nm_ctx* ctx, int slot, const float* pts, const float* views, int64_t n,
                          int32_t views_per_ray, float* raw, void* stash_x, void* stash_f, void* stash_v,
@@ -102,6 +103,10 @@ int nm_mlp_forward_train(nm_ctx* ctx, int slot, const float* pts, const float* v
  * caller's BLAS), the bias gradients the column sums of g_l. */
 int nm_mlp_backward(nm_ctx* ctx, int slot, const float* d_raw, const float* loss_scale, int64_t n,
                     const void* stash_v, const void* stash_m, void* g_pre, void* g_f, void* g_v, void* stream);
+
+/* Bias gradients (the `.bias.grad` torch autograd accumulates): out[p][c] = sum_i src[p][i][c] over fp16 planes
+ * src [planes][n][width] (width even, <= 256), fp32 accumulation.  out is overwritten. */
+int nm_colsum_f16(nm_ctx* ctx, const void* src, int32_t planes, int64_t n, int32_t width, float* out, void* stream);
 
 /* Same network, but the sample positions are generated in-kernel: pts[r,s] = o[r] + d[r]*z[r,s],
  * views = d[r] (utils/ray_utils.py:131-132).  o,d: [R,3]; z: [R,S]; raw: [R,S,4]. */

@@ -117,29 +117,44 @@ class _JoinerMLP(torch.autograd.Function):
         return (None, None, None, *out)
 
 
+def _colsum(ctx, t):
+    """[planes, n, width] fp16 -> [planes, width] fp32 column sums (csrc/mlp_tc_bwd.cu: k_colsum_f16)."""
+    planes, n, width = t.shape
+    out = torch.empty(planes, width, device=t.device, dtype=torch.float32)
+    ctx.check(ctx.lib.nm_colsum_f16(ctx.h, _p(t), planes, n, width, _p(out), _stream()))
+    return out
+
+
 def _weight_grads(joiner, stash, g, g_pre, g_f, g_v, inv):
-    """dW = g^T @ layer input, db = column sums; g_* are fp16 and carry the loss scale 1/inv."""
+    """dW = g^T @ layer input (cuBLAS, K = n, fp16 operands / fp32 accumulate); g_* carry the loss scale 1/inv.
+    Every GEMM operand is a whole, 16-byte aligned stash plane (the 64-/32-channel encodings including their
+    padding, the [n,8]-padded dL/d raw), which keeps cuBLAS on its tensor-core kernels; the encodings' constant
+    1.0 channel returns the bias gradients of pts_linears.0/.5 and views_linears.0 as an extra GEMM column, the
+    other bias gradients are column sums (k_colsum_f16)."""
     sx, sf, sv, spe, sdpe, _ = stash
-    n_pe, n_dpe = joiner.pos_pe.out_dim, joiner.dir_pe.out_dim
-    pe, dpe = spe[:, :n_pe], sdpe[:, :n_dpe]
+    ctx = _ctx_for(g)
+    n_pe, n_dpe = joiner.pos_pe.out_dim, joiner.dir_pe.out_dim          # 63, 27: the 1.0 channel sits right after
     grads = {}
-    gh = (g * (1.0 / inv)).half()                                         # [n,4] scaled like the chain outputs
-    grads['rgb_linear.weight'] = _mm32(gh[:, :3].t(), sv) * inv
+    g8 = torch.zeros(g.shape[0], 8, device=g.device, dtype=torch.float16)
+    g8[:, :4] = g * (1.0 / inv)
+    g8t = g8.t()
+    grads['rgb_linear.weight'] = _mm32(g8t, sv)[:3] * inv
     grads['rgb_linear.bias'] = g[:, :3].sum(0)
-    grads['alpha_linear.weight'] = _mm32(gh[:, 3:4].t(), sx[7]) * inv
+    grads['alpha_linear.weight'] = _mm32(g8t, sx[7])[3:4] * inv
     grads['alpha_linear.bias'] = g[:, 3].sum().reshape(1)
     gvt = g_v.t()
-    grads['views_linears.0.weight'] = torch.cat([_mm32(gvt, sf), _mm32(gvt, dpe)], 1) * inv
-    grads['views_linears.0.bias'] = g_v.sum(0, dtype=torch.float32) * inv
+    wd = _mm32(gvt, sdpe) * inv                                           # [128, 32]
+    grads['views_linears.0.weight'] = torch.cat([_mm32(gvt, sf) * inv, wd[:, :n_dpe]], 1)
+    grads['views_linears.0.bias'] = wd[:, n_dpe]
     grads['feature_linear.weight'] = _mm32(g_f.t(), sx[7]) * inv
-    grads['feature_linear.bias'] = g_f.sum(0, dtype=torch.float32) * inv
-    db = g_pre.sum(1, dtype=torch.float32) * inv                          # [8,256]
+    grads['feature_linear.bias'] = _colsum(ctx, g_f[None])[0] * inv
+    db = _colsum(ctx, g_pre) * inv                                        # [8,256] (rows 0 and 5 also come from the GEMMs)
     for l in range(8):
         gt = g_pre[l].t()
         if l == 0:
-            w = _mm32(gt, pe)
+            w = _mm32(gt, spe)[:, :n_pe]
         elif l == 5:
-            w = torch.cat([_mm32(gt, pe), _mm32(gt, sx[4])], 1)
+            w = torch.cat([_mm32(gt, spe)[:, :n_pe], _mm32(gt, sx[4])], 1)
         else:
             w = _mm32(gt, sx[l - 1])
         grads['pts_linears.%d.weight' % l] = w * inv

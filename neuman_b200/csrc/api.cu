@@ -325,6 +325,14 @@ extern "C" int nm_mlp_backward(nm_ctx* ctx, int slot, const float* d_raw, const 
                         (__half*)g_pre, (__half*)g_f, (__half*)g_v, (cudaStream_t)stream);
 }
 
+extern "C" int nm_colsum_f16(nm_ctx* ctx, const void* src, int32_t planes, int64_t n, int32_t width, float* out, void* stream) {
+  if (!ctx) return NM_ERR_INVALID;
+  if (planes < 0 || n < 0 || width <= 0 || width > 256 || (width & 1)) NM_FAIL(ctx, NM_ERR_INVALID, "nm_colsum_f16: bad shape");
+  if (planes == 0) return NM_OK;
+  if (!out || (n > 0 && !src)) NM_FAIL(ctx, NM_ERR_INVALID, "nm_colsum_f16: null argument");
+  return nm_impl_colsum_f16(ctx, (const __half*)src, planes, n, width, out, (cudaStream_t)stream);
+}
+
 extern "C" int nm_mlp_forward_rays(nm_ctx* ctx, int slot, int mode, const float* origins, const float* dirs,
                                    const float* z, int64_t R, int32_t S, float* raw, void* stream) {
   if (!ctx) return NM_ERR_INVALID;

@@ -27,6 +27,7 @@
 #include "nm_internal.cuh"
 #include "nm_pe.cuh"
 #include "tc_common.cuh"
+#include <string.h>
 // ---------------------------------------------------------------------------------------------
 // Plan: which slabs a step consumes, where they live in the packed image.
 // ---------------------------------------------------------------------------------------------
@@ -76,9 +77,10 @@ struct TcParams {
   __half* st_x;             // [8][n][256] post-ReLU outputs of layers 0..7
   __half* st_f;             // [n][256]    feature_linear output
   __half* st_v;             // [n][128]    views layer post-ReLU
-  __half* st_pe;            // [n][64]     position encoding (channel 63 = 0)
-  __half* st_dpe;           // [n][32]     direction encoding (channels 27..31 = 0)
+  __half* st_pe;            // [n][64]     position encoding (channel 63 = 1: bias column)
+  __half* st_dpe;           // [n][32]     direction encoding (channel 27 = 1: bias column, 28..31 = 0)
   uint32_t* st_m;           // [8][n][8]   sign words: bit c of row = [layer output c > 0]
+  CUtensorMap map_x, map_f, map_v;   // TMA store maps of st_x / st_f / st_v (kTrain only)
   long long* trace;         // optional debug timeline (tools/tc_trace.py): [cta<2][role<2][event<4][256] clock64 stamps
 };
 
@@ -259,7 +261,7 @@ __device__ __forceinline__ void epi_step(uint32_t t_lane, int cbase, int ncols, 
   } while (0)
 
 template <int kPair, bool kConst, bool kTrain>
-__global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcParams P) {
+__global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __grid_constant__ TcParams P) {
   using C = TcCfg<kPair>;
   constexpr int NT = C::NT, NSLOT = C::NSLOT;
   extern __shared__ uint8_t smem_dyn[];
@@ -434,7 +436,9 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
       if (kTrain && tile_valid(round, g)) {
         uint4* dst = reinterpret_cast<uint4*>(P.st_pe + (size_t)sample_index(round, g) * 64);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_uint4(pe_pos[4 * j], pe_pos[4 * j + 1], pe_pos[4 * j + 2], pe_pos[4 * j + 3]);
+        for (int j = 0; j < 7; ++j) dst[j] = make_uint4(pe_pos[4 * j], pe_pos[4 * j + 1], pe_pos[4 * j + 2], pe_pos[4 * j + 3]);
+        // the stash's padding channel 63 carries 1.0: g^T @ stash then yields the bias gradient as column 63
+        dst[7] = make_uint4(pe_pos[28], pe_pos[29], pe_pos[30], pe_pos[31] | 0x3C000000u);
       }
     };
     auto encode_dir = [&](long long round) {
@@ -447,7 +451,8 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
       if (kTrain && tile_valid(round, g)) {
         uint4* dst = reinterpret_cast<uint4*>(P.st_dpe + (size_t)sample_index(round, g) * 32);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pe_dir[4 * j], pe_dir[4 * j + 1], pe_dir[4 * j + 2], pe_dir[4 * j + 3]);
+        for (int j = 0; j < 3; ++j) dst[j] = make_uint4(pe_dir[4 * j], pe_dir[4 * j + 1], pe_dir[4 * j + 2], pe_dir[4 * j + 3]);
+        dst[3] = make_uint4(pe_dir[12], pe_dir[13] | 0x3C000000u, pe_dir[14], pe_dir[15]);      // channel 27 := 1.0 (bias column)
       }
     };
     if (n_rounds > 0 && pe_owner) encode_pos(0);
@@ -480,21 +485,40 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const TcPar
           if (t == 0 && etid == 0) TC_TRACE(1, 0, nstep);
           if (s < 10) {
             const int nh = (s == 9) ? 64 : 128;         // columns drained by this thread
-            __half* grow = nullptr;
-            if (kTrain && tile_valid(round, t)) {
-              const long long i = sample_index(round, t);
-              grow = s < 8 ? P.st_x + ((size_t)s * P.in.n + i) * 256 : (s == 8 ? P.st_f + (size_t)i * 256 : P.st_v + (size_t)i * 128);
-            }
+            __half* grow = nullptr;                     // per-thread HBM stores: unused, the stash goes out by TMA below
+            // this warp's slice of the tile's activation buffer is the source of the TMA store issued one step
+            // ago: it must have been read before the slice is overwritten (the other tile's store may still fly)
+            if (kTrain) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
             uint4 signs = make_uint4(0, 0, 0, 0);
             if (s == 7) epi_step<true, true, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row, grow, signs);
             else if (s == 8) epi_step<false, false, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row, grow, signs);
             else epi_step<true, false, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row, grow, signs);
-            if (kTrain && s < 8 && grow)
+            if (kTrain && s < 8 && tile_valid(round, t))
               reinterpret_cast<uint4*>(P.st_m + ((size_t)s * P.in.n + sample_index(round, t)) * 8)[g] = signs;
             if (s == 7 && g == 1) s_alpha[t * 128 + row] = (alpha[t][0] + alpha[t][1]) + (alpha[t][2] + alpha[t][3]);
             if (s == 4 && g == t) { wait_pe_slot(round, 1, t); store_row_swizzled(pebuf, row, pe_pos, 8); }   // skip input (:131)
             if (s == 8 && g == t) { wait_pe_slot(round, 2, t); store_row_swizzled(pebuf, row, pe_dir, 4); }   // view dirs (:137)
             if (t == 0 && etid == 0) TC_TRACE(1, 1, nstep);
+            if (kTrain) {
+              // activation stash: this warp's 32 rows x (128 | 64) columns, straight from the swizzled A buffer
+              fence_async_smem();
+              __syncwarp();
+              const long long i0 = sample_index(round, t) - lane;            // first row of this warp
+              if (lane == 0 && i0 < P.in.n) {
+                const uint32_t src = sbase + C::OFF_ACT + t * 4 * TC_KB_BYTES + quad * 32 * 128;
+                if (s < 9) {
+                  const CUtensorMap* m = s < 8 ? &P.map_x : &P.map_f;
+                  tma_store_3d(m, src + (2 * g) * TC_KB_BYTES, 128 * g, (int)i0, s < 8 ? s : 0);
+                  tma_store_3d(m, src + (2 * g + 1) * TC_KB_BYTES, 128 * g + 64, (int)i0, s < 8 ? s : 0);
+                } else {
+                  tma_store_3d(&P.map_v, src + g * TC_KB_BYTES, 64 * g, (int)i0, 0);
+                }
+                tma_store_commit();
+                // steps 8 and 9 hand this slice to another warp (the column split changes from 128 to 64 per
+                // warpgroup and back): the store must have finished reading before anyone is told to go on
+                if (s >= 8) tma_store_wait_read<0>();
+              }
+            }
             publish(t);
             if (t == 0 && etid == 0) TC_TRACE(1, 2, nstep);
           } else {
@@ -693,6 +717,13 @@ int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* 
   P.trace = nullptr;
   P.st_x = stash ? stash->x : nullptr; P.st_f = stash ? stash->f : nullptr; P.st_v = stash ? stash->v : nullptr;
   P.st_pe = stash ? stash->pe : nullptr; P.st_dpe = stash ? stash->dpe : nullptr; P.st_m = stash ? stash->m : nullptr;
+  memset(&P.map_x, 0, 3 * sizeof(CUtensorMap));
+  if (stash) {
+    if (n >= (int64_t)0x7fff0000) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward_train: n too large for one call");
+    if (tc_make_store_map(&P.map_x, stash->x, 8, (uint64_t)n, 256) || tc_make_store_map(&P.map_f, stash->f, 1, (uint64_t)n, 256) ||
+        tc_make_store_map(&P.map_v, stash->v, 1, (uint64_t)n, 128))
+      NM_FAIL(ctx, NM_ERR_CUDA, "nm_mlp_forward_train: cuTensorMapEncodeTiled failed");
+  }
   if (const char* e = getenv("NEUMAN_TC_TRACE")) P.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   const int slot = (int)(&net - ctx->nets);
   P.cslot = (slot >= 0 && slot < TC_CONST_NETS) ? slot : 0;

@@ -47,6 +47,7 @@ struct BwParams {
   __half* g_f;              // [n][256]    out: S * dL/d feature
   __half* g_v;              // [n][128]    out: S * dL/d(pre-activation of views_linears.0)
   long long n, n_tiles;
+  CUtensorMap map_pre, map_f;   // TMA store maps of g_pre / g_f
 };
 
 // 16 accumulator columns [c0, c0+16) of one row: (+ rank-1 alpha term), ReLU mask from sign bits, pack,
@@ -101,7 +102,7 @@ __device__ __forceinline__ void bw_step(uint32_t t_lane, int cbase, float da, co
 }
 
 template <int kPair>
-__global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const BwParams P) {
+__global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const __grid_constant__ BwParams P) {
   using C = BwCfg<kPair>;
   constexpr int NT = C::NT, NSLOT = C::NSLOT;
   extern __shared__ uint8_t smem_dyn[];
@@ -298,19 +299,37 @@ __global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const B
           const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + t * 256;
           mbar_wait(bar_tfull(t), nstep & 1);
           tc_fence_after();
+          // steps 0..7 leave through TMA from the A buffer (below); the last step, which must not touch the A
+          // buffer, stores its rows to HBM directly
           __half* grow = nullptr;
-          if (tile_valid(round, t)) {
-            const long long i = sample_index(round, t);
-            grow = b == 0 ? P.g_f + (size_t)i * 256 : P.g_pre + ((size_t)(8 - b) * P.n + i) * 256;
-          }
+          if (b == BW_STEPS - 1 && tile_valid(round, t)) grow = P.g_pre + (size_t)sample_index(round, t) * 256;
+          // this warp's slice is the source of the store issued one step ago (the other tile's may still fly)
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
           // the last step's result (dpre of layer 0) only goes to HBM: the tile's A buffer already belongs to the
           // next round's head, which the other warpgroup may be writing
           if (b == 0) bw_step<false, false, true>(t_lane, g * 128, 0.f, s_walpha, mcur[t], act, row, grow);
           else if (b == 1) bw_step<true, true, true>(t_lane, g * 128, da[t], s_walpha, mcur[t], act, row, grow);
           else if (b < BW_STEPS - 1) bw_step<false, true, true>(t_lane, g * 128, 0.f, s_walpha, mcur[t], act, row, grow);
           else bw_step<false, true, false>(t_lane, g * 128, 0.f, s_walpha, mcur[t], act, row, grow);
-          if (b < BW_STEPS - 1) publish(t);
-          else tc_fence_before();
+          if (b < BW_STEPS - 1) {
+            fence_async_smem();
+            __syncwarp();
+            const long long i0 = sample_index(round, t) - lane;              // first row of this warp
+            if (lane == 0 && i0 < P.n) {
+              const uint32_t src = sbase + C::OFF_ACT + (t * 4 + 2 * g) * TC_KB_BYTES + quad * 32 * 128;
+              const CUtensorMap* m = b == 0 ? &P.map_f : &P.map_pre;
+              tma_store_3d(m, src, 128 * g, (int)i0, b == 0 ? 0 : 8 - b);
+              tma_store_3d(m, src + TC_KB_BYTES, 128 * g + 64, (int)i0, b == 0 ? 0 : 8 - b);
+              tma_store_commit();
+              // after step 7 the tile's A buffer passes to the next round's head, written by the other
+              // warpgroup: the store must have finished reading before anyone is told to go on
+              if (b == BW_STEPS - 2) tma_store_wait_read<0>();
+            }
+            publish(t);
+          } else {
+            tc_fence_before();
+          }
         }
         if (b == 4 && round + 1 < n_rounds) build_head(round + 1);
       }
@@ -359,6 +378,44 @@ __global__ void k_bw_pack(BwPackSrc S, int kpair, uint32_t image_bytes, __half* 
   const int kk = chunk * 8 + ((in_slab & 15) >> 1);
   const int n = rank * (256 / kpair) + n_local;
   out[(size_t)rank * (image_bytes / 2) + e] = __float2half_rn(bw_src_weight(S, b, n, kb, kk));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bias gradients: column sums of fp16 gradient planes, fp32 accumulation.  HBM-bound (reads each plane once).
+// grid = (row chunks, planes); a block owns `width` columns (2 per thread) and strides over its rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_colsum_f16(const __half* __restrict__ src, long long n, int width,
+                                                    long long rows_per_block, float* __restrict__ out) {
+  const int plane = blockIdx.y;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(n, r0 + rows_per_block);
+  const int c2 = threadIdx.x;                       // column pair
+  if (2 * c2 >= width) return;
+  const __half2* p = reinterpret_cast<const __half2*>(src + ((size_t)plane * n + r0) * width) + c2;
+  const size_t stride = (size_t)width / 2;
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  long long r = r0;
+  for (; r + 4 <= r1; r += 4) {                     // 4 independent loads in flight per thread
+    const float2 v0 = __half22float2(p[0]), v1 = __half22float2(p[stride]);
+    const float2 v2 = __half22float2(p[2 * stride]), v3 = __half22float2(p[3 * stride]);
+    a0 += v0.x; a1 += v0.y; b0 += v1.x; b1 += v1.y;
+    a0 += v2.x; a1 += v2.y; b0 += v3.x; b1 += v3.y;
+    p += 4 * stride;
+  }
+  for (; r < r1; ++r) { const float2 v = __half22float2(p[0]); a0 += v.x; a1 += v.y; p += stride; }
+  atomicAdd(out + (size_t)plane * width + 2 * c2, a0 + b0);
+  atomicAdd(out + (size_t)plane * width + 2 * c2 + 1, a1 + b1);
+}
+
+int nm_impl_colsum_f16(nm_ctx* ctx, const __half* src, int planes, int64_t n, int width, float* out, cudaStream_t st) {
+  NM_CHECK_CUDA(ctx, cudaMemsetAsync(out, 0, (size_t)planes * width * sizeof(float), st));
+  const int chunks = max(1, (ctx->sm_count * 16) / max(planes, 1));
+  long long rows_per_block = (n + chunks - 1) / chunks;
+  if (rows_per_block < 64) rows_per_block = 64;
+  dim3 grid((unsigned)((n + rows_per_block - 1) / rows_per_block), planes);
+  k_colsum_f16<<<grid, 128, 0, st>>>(src, n, width, rows_per_block, out);
+  NM_CHECK_LAUNCH(ctx);
+  return NM_OK;
 }
 
 static int bw_pair_mode() {
@@ -428,5 +485,8 @@ int nm_tc_backward(nm_ctx* ctx, NmNet& net, const float* d_raw, const float* sca
   P.g_pre = g_pre; P.g_f = g_f; P.g_v = g_v;
   P.n = n;
   P.n_tiles = (n + 128 * kpair - 1) / (128 * kpair);
+  if (n >= (int64_t)0x7fff0000) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_backward: n too large for one call");
+  if (tc_make_store_map(&P.map_pre, g_pre, 8, (uint64_t)n, 256) || tc_make_store_map(&P.map_f, g_f, 1, (uint64_t)n, 256))
+    NM_FAIL(ctx, NM_ERR_CUDA, "nm_mlp_backward: cuTensorMapEncodeTiled failed");
   return kpair == 2 ? launch_bwd<2>(ctx, P, st) : launch_bwd<1>(ctx, P, st);
 }

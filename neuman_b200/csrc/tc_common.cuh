@@ -158,3 +158,41 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi, bool relu) {
   return d;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// TMA tensor stores (shared -> global) of activation blocks.  The UMMA SWIZZLE_128B K-major block layout is the
+// TMA SWIZZLE_128B box layout, so a warp's 32 rows x 64 columns of an activation k-block (4 KB, contiguous in
+// shared memory) go out as one box and land row-major in the HBM plane.
+// ---------------------------------------------------------------------------------------------
+#include <cuda.h>
+
+// [planes][rows][width] fp16, box = 64 columns x 32 rows x 1 plane
+inline int tc_make_store_map(CUtensorMap* map, const void* base, uint64_t planes, uint64_t rows, uint32_t width) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -1;
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[3] = {width, rows, planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)width * 2, (cuuint64_t)rows * width * 2};
+  const cuuint32_t box[3] = {64, 32, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t smem_src, int col, int row, int plane) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(smem_src),
+               "r"(col), "r"(row), "r"(plane) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the issuing thread waits until at most N of its committed store groups still read shared memory
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }

@@ -15,10 +15,21 @@ import sys
 import torch
 
 
-def install(reference_root=None):
+def install(reference_root=None, train_bkg=False):
+    """train_bkg=True additionally routes the background trainer's autograd path
+    (trainers/vanilla_nerf_trainer.py:45-96: Joiner.forward and raw2outputs with gradients recording) to the
+    CUDA training kernels.  Leave it off for the human trainer, whose loss differentiates through the sample
+    positions (not built: the reference torch path keeps serving it)."""
     if reference_root and reference_root not in sys.path:
         sys.path.insert(0, reference_root)
-    from . import ops, render
+    from . import autograd, ops, render
+
+    def on_cuda(*ts):
+        return all(isinstance(t, torch.Tensor) and t.is_cuda for t in ts)
+
+    def trainable_arch(j):
+        n = j.nerf
+        return (n.use_viewdirs and len(n.pts_linears) == 8 and tuple(n.skips) == (4,) and n.pts_linears[1].weight.shape == (256, 256))
     ru = importlib.import_module("utils.render_utils")
     ry = importlib.import_module("utils.ray_utils")
     mv = importlib.import_module("models.vanilla")
@@ -31,7 +42,10 @@ def install(reference_root=None):
     def joiner_forward(self, input_pts, input_views=None):
         if input_views is not None and on_cuda_nograd(input_pts, input_views) and self.nerf.use_viewdirs:
             return ops.joiner_forward(self, input_pts, input_views)
-        return ref_forward(self, input_pts, input_views)          # training / CPU: reference torch path
+        if (train_bkg and input_views is not None and torch.is_grad_enabled() and on_cuda(input_pts, input_views)
+                and trainable_arch(self) and not input_pts.requires_grad):
+            return autograd.joiner_forward(self, input_pts, input_views)
+        return ref_forward(self, input_pts, input_views)          # other training / CPU: reference torch path
     mv.Joiner.forward = joiner_forward
 
     ref_raw2outputs = ru.raw2outputs
@@ -39,6 +53,8 @@ def install(reference_root=None):
     def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkg=True):
         if on_cuda_nograd(raw, z_vals, rays_d):
             return ops.raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkg)
+        if train_bkg and torch.is_grad_enabled() and on_cuda(raw, z_vals, rays_d) and not z_vals.requires_grad:
+            return autograd.raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkg)
         return ref_raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkg)
     ru.raw2outputs = raw2outputs
 
