@@ -104,6 +104,13 @@ int nm_mlp_forward_train(nm_ctx* ctx, int slot, const float* pts, const float* v
 int nm_mlp_backward(nm_ctx* ctx, int slot, const float* d_raw, const float* loss_scale, int64_t n,
                     const void* stash_v, const void* stash_m, void* g_pre, void* g_f, void* g_v, void* stream);
 
+/* Adjoint of Embedder.forward (models/vanilla.py:82-92) of net `slot`: which = 0 position encoding, 1 direction
+ * encoding.  x: the encoder input [n,3] (or [n/group,3] when group > 0, as nm_mlp_forward's views_per_ray);
+ * d_enc: [n][ld] fp32 dL/d(encoding), ld >= encoding width; inv_scale: optional device scalar multiplied into the
+ * result; d_x: [n,3] out (per sample, also when the input is shared by a group: sum over the group is the caller's). */
+int nm_pe_backward(nm_ctx* ctx, int slot, int32_t which, const float* x, int64_t group, const float* d_enc,
+                   int32_t ld, const float* inv_scale, int64_t n, float* d_x, void* stream);
+
 /* Bias gradients (the `.bias.grad` torch autograd accumulates): out[p][c] = sum_i src[p][i][c] over fp16 planes
  * src [planes][n][width] (width even, <= 256), fp32 accumulation.  out is overwritten. */
 int nm_colsum_f16(nm_ctx* ctx, const void* src, int32_t planes, int64_t n, int32_t width, float* out, void* stream);

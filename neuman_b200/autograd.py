@@ -71,8 +71,9 @@ class _JoinerMLP(torch.autograd.Function):
     on the tensor cores and writes S * dL/d(pre-activation) of every layer in fp16 (S = power-of-two loss scale
     chosen from max|dL/d raw| on the device); the weight gradients are the K = n GEMMs  g_l^T @ input_l  over the
     stash (cuBLAS through torch.mm, fp16 operands / fp32 accumulate) and the bias gradients column sums.
-    Gradients are produced for the network parameters; sample positions/directions are constants of the step
-    (as in the reference's NeRF trainer, trainers/vanilla_nerf_trainer.py:45-96).
+    Gradients go to the network parameters and, when they require grad, to the sample positions / directions
+    (dL/d encoding by two small cuBLAS GEMMs on the gradient planes, then k_pe_backward), which is what the human
+    trainer's differentiable warp and offset nets consume (trainers/human_nerf_trainer.py:241-278).
     NEUMAN_BWD_TORCH=1 evaluates the same chain with torch GEMMs from the same stash (debug / cross-check).
 
     The gradient is the exact adjoint of the fp16-operand forward: ReLU masks are those of the fp16 activations,
@@ -95,26 +96,53 @@ class _JoinerMLP(torch.autograd.Function):
                                                    _p(spe), _p(sdpe), _p(sm), _stream()))
         fctx.joiner = joiner
         fctx.stash = (sx, sf, sv, spe, sdpe, sm)
-        fctx.save_for_backward(*params)
+        fctx.save_for_backward(pts, views, *params)
         return raw
 
     @staticmethod
     def backward(fctx, g_raw):
         stash = fctx.stash
         fctx.stash = None
-        nerf = fctx.joiner.nerf
-        names = [k for k, _ in nerf.named_parameters()]
-        P = dict(zip(names, fctx.saved_tensors))
+        joiner = fctx.joiner
+        names = [k for k, _ in joiner.nerf.named_parameters()]
+        pts, views = fctx.saved_tensors[:2]
+        P = dict(zip(names, fctx.saved_tensors[2:]))
         g = g_raw.reshape(-1, 4).float().contiguous()
+        need_w = any(fctx.needs_input_grad[3:])
+        d_pts = d_views = None
         if g.shape[0] == 0:
             grads = {k: torch.zeros_like(v) for k, v in P.items()}
-        elif _use_torch_chain():
-            grads = _chain_torch(fctx.joiner, P, stash, g)
+            d_pts, d_views = torch.zeros_like(pts), torch.zeros_like(views)
         else:
-            grads = _chain_kernel(fctx.joiner, P, stash, g)
+            chain = _chain_torch if _use_torch_chain() else _chain_kernel
+            g_pre, g_f, g_v, inv = chain(joiner, P, stash, g)
+            grads = _weight_grads(joiner, stash, g, g_pre, g_f, g_v, inv) if need_w else {}
+            if fctx.needs_input_grad[0]:
+                d_pts = _input_grad(joiner, P, pts, 0, ((g_pre[0], 'pts_linears.0.weight', 0), (g_pre[5], 'pts_linears.5.weight', 0)), inv)
+            if fctx.needs_input_grad[1]:
+                d_views = _input_grad(joiner, P, views, 1, ((g_v, 'views_linears.0.weight', 256),), inv)
         out = [grads[k].reshape(P[k].shape).to(P[k].dtype) if fctx.needs_input_grad[3 + i] else None
                for i, k in enumerate(names)]
-        return (None, None, None, *out)
+        return (d_pts, d_views, None, *out)
+
+
+def _input_grad(joiner, P, x, which, terms, inv):
+    """dL/d(pts) or dL/d(views): dL/d(encoding) = sum over the layers that read it of g_l @ W_l[:, encoding columns]
+    (cuBLAS, fp16 operands, fp32 out), then the adjoint of Embedder.forward (k_pe_backward)."""
+    ctx = _ctx_for(x)
+    slot = ops.net_slot(joiner, ctx)
+    width = (joiner.pos_pe if which == 0 else joiner.dir_pe).out_dim
+    ld = (width + 31) // 32 * 32
+    d_enc = None
+    for gl, name, col0 in terms:
+        w = torch.zeros(gl.shape[1], ld, device=x.device, dtype=torch.float16)
+        w[:, :width] = P[name].detach()[:, col0:col0 + width]
+        t = _mm32(gl, w)
+        d_enc = t if d_enc is None else d_enc + t
+    n = x.shape[0]
+    d_x = torch.empty(n, 3, device=x.device, dtype=torch.float32)
+    ctx.check(ctx.lib.nm_pe_backward(ctx.h, slot, which, _p(x), 0, _p(d_enc), ld, _p(inv.contiguous()), n, _p(d_x), _stream()))
+    return d_x
 
 
 def _colsum(ctx, t):
@@ -172,7 +200,7 @@ def _chain_kernel(joiner, P, stash, g):
     g_pre, g_f, g_v = torch.empty(8, n, 256, **h), torch.empty(n, 256, **h), torch.empty(n, 128, **h)
     ctx.check(ctx.lib.nm_mlp_backward(ctx.h, slot, _p(g), _p(scale), n, _p(sv), _p(sm), _p(g_pre), _p(g_f), _p(g_v),
                                       _stream()))
-    return _weight_grads(joiner, stash, g, g_pre, g_f, g_v, 1.0 / scale)
+    return g_pre, g_f, g_v, 1.0 / scale
 
 
 def _chain_torch(joiner, P, stash, g):
@@ -195,14 +223,15 @@ def _chain_torch(joiner, P, stash, g):
         if l > 0:
             w = wh('pts_linears.%d.weight' % l)
             dX = _mm32(g_pre[l], w[:, n_pe:].contiguous() if l == 5 else w)
-    return _weight_grads(joiner, stash, g, g_pre, g_f, g_v, inv)
+    return g_pre, g_f, g_v, inv
 
 
 def joiner_forward(joiner, input_pts, input_views):
-    """Joiner.forward (models/vanilla.py:162-166) with gradients to the network parameters."""
+    """Joiner.forward (models/vanilla.py:162-166) with gradients to the network parameters and, when they require
+    grad, to input_pts / input_views."""
     shape = input_pts.shape[:-1]
-    pts = _f32(input_pts).reshape(-1, 3)
-    views = _f32(input_views, pts.device).reshape(-1, 3)
+    pts = input_pts.float().contiguous().reshape(-1, 3)          # autograd-tracked views of the inputs
+    views = input_views.to(pts.device).float().contiguous().reshape(-1, 3)
     assert views.shape[0] == pts.shape[0], "input_views must match input_pts"
     params = [p for _, p in joiner.nerf.named_parameters()]
     return _JoinerMLP.apply(pts, views, joiner, *params).reshape(*shape, 4)

@@ -325,6 +325,20 @@ extern "C" int nm_mlp_backward(nm_ctx* ctx, int slot, const float* d_raw, const 
                         (__half*)g_pre, (__half*)g_f, (__half*)g_v, (cudaStream_t)stream);
 }
 
+extern "C" int nm_pe_backward(nm_ctx* ctx, int slot, int32_t which, const float* x, int64_t group, const float* d_enc,
+                              int32_t ld, const float* inv_scale, int64_t n, float* d_x, void* stream) {
+  if (!ctx) return NM_ERR_INVALID;
+  if (slot < 0 || slot >= NM_MAX_NET_SLOTS || !ctx->nets[slot].packed)
+    NM_FAIL(ctx, NM_ERR_STATE, "nm_pe_backward: net slot not packed");
+  if ((which != 0 && which != 1) || n < 0 || group < 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_pe_backward: bad argument");
+  const NmNet& net = ctx->nets[slot];
+  const int width = 3 + 6 * (which == 0 ? net.desc.pos_n_freqs : net.desc.dir_n_freqs);
+  if (ld < width) NM_FAIL(ctx, NM_ERR_INVALID, "nm_pe_backward: ld smaller than the encoding width");
+  if (n == 0) return NM_OK;
+  if (!x || !d_enc || !d_x) NM_FAIL(ctx, NM_ERR_INVALID, "nm_pe_backward: null argument");
+  return nm_impl_pe_backward(ctx, net, which, x, group, d_enc, ld, inv_scale, n, d_x, (cudaStream_t)stream);
+}
+
 extern "C" int nm_colsum_f16(nm_ctx* ctx, const void* src, int32_t planes, int64_t n, int32_t width, float* out, void* stream) {
   if (!ctx) return NM_ERR_INVALID;
   if (planes < 0 || n < 0 || width <= 0 || width > 256 || (width & 1)) NM_FAIL(ctx, NM_ERR_INVALID, "nm_colsum_f16: bad shape");

@@ -12,6 +12,7 @@
 // memory as the next step's A operand.  The ReLU masks come from the forward's 256-bit sign words.
 // Gradients w.r.t. the sample positions are not produced (the trainers treat samples as constants).
 #include "nm_internal.cuh"
+#include "nm_pe.cuh"
 #include "tc_common.cuh"
 
 #define BW_STEPS 9
@@ -414,6 +415,47 @@ int nm_impl_colsum_f16(nm_ctx* ctx, const __half* src, int planes, int64_t n, in
   if (rows_per_block < 64) rows_per_block = 64;
   dim3 grid((unsigned)((n + rows_per_block - 1) / rows_per_block), planes);
   k_colsum_f16<<<grid, 128, 0, st>>>(src, n, width, rows_per_block, out);
+  NM_CHECK_LAUNCH(ctx);
+  return NM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adjoint of Embedder.forward (models/vanilla.py:82-92): d_x = J^T d_enc with
+//   posenc: enc = [x, sin(f_k x), cos(f_k x)]_k          rotate: enc = [x, sin(x B^T), cos(x B^T)]
+// One thread per sample; sin/cos recomputed in fp32 exactly as the fp32 forward does (nm_pe_pair).
+// d_enc rows are `ld` floats apart and carry a scale whose inverse is *inv_scale (device scalar, may be null).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pe_backward(NmPeSpec pe, const float* __restrict__ x, long long group, const float* __restrict__ d_enc,
+                              int ld, const float* __restrict__ inv_scale, long long n, float* __restrict__ d_x) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long xi = group > 0 ? i / group : i;
+  const float xv[3] = {x[3 * xi], x[3 * xi + 1], x[3 * xi + 2]};
+  const float* g = d_enc + (size_t)i * ld;
+  float dx[3] = {g[0], g[1], g[2]};
+  const int nq = 3 * pe.n_freqs;
+  for (int q = 0; q < nq; ++q) {
+    float sn, cs;
+    int c_sin, c_cos;
+    nm_pe_pair(pe, xv, q, sn, cs, c_sin, c_cos);
+    const float w = cs * g[c_sin] - sn * g[c_cos];
+    if (pe.kind == NM_PE_ROTATE) {
+      const float* b = pe.table + 3 * q;
+      dx[0] = fmaf(w, b[0], dx[0]); dx[1] = fmaf(w, b[1], dx[1]); dx[2] = fmaf(w, b[2], dx[2]);
+    } else {
+      const int k = q / 3, d = q - 3 * k;
+      dx[d] = fmaf(w, pe.table[k], dx[d]);
+    }
+  }
+  const float sc = inv_scale ? *inv_scale : 1.f;
+  d_x[3 * i] = dx[0] * sc; d_x[3 * i + 1] = dx[1] * sc; d_x[3 * i + 2] = dx[2] * sc;
+}
+
+int nm_impl_pe_backward(nm_ctx* ctx, const NmNet& net, int which, const float* x, int64_t group, const float* d_enc, int ld,
+                        const float* inv_scale, int64_t n, float* d_x, cudaStream_t st) {
+  NmPeSpec pe = which == 0 ? NmPeSpec{net.desc.pos_pe_kind, net.desc.pos_n_freqs, net.f32 + net.o_pos_bv}
+                           : NmPeSpec{net.desc.dir_pe_kind, net.desc.dir_n_freqs, net.f32 + net.o_dir_bv};
+  k_pe_backward<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pe, x, group, d_enc, ld, inv_scale, n, d_x);
   NM_CHECK_LAUNCH(ctx);
   return NM_OK;
 }

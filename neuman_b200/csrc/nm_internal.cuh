@@ -132,6 +132,8 @@ struct NmTrainStash {
   __half* dpe;   // [n][32]     direction encoding
   uint32_t* m;   // [8][n][8]   ReLU sign words of pts_linears 0..7 (bit c of the 256-bit row = [X > 0])
 };
+int nm_impl_pe_backward(nm_ctx* ctx, const NmNet& net, int which, const float* x, int64_t group, const float* d_enc, int ld,
+                        const float* inv_scale, int64_t n, float* d_x, cudaStream_t st);
 int nm_impl_colsum_f16(nm_ctx* ctx, const __half* src, int planes, int64_t n, int width, float* out, cudaStream_t st);
 int nm_tc_backward(nm_ctx* ctx, NmNet& net, const float* d_raw, const float* scale, int64_t n, const __half* st_v,
                    const uint32_t* st_m, __half* g_pre, __half* g_f, __half* g_v, cudaStream_t st);

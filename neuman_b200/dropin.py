@@ -15,11 +15,12 @@ import sys
 import torch
 
 
-def install(reference_root=None, train_bkg=False):
-    """train_bkg=True additionally routes the background trainer's autograd path
-    (trainers/vanilla_nerf_trainer.py:45-96: Joiner.forward and raw2outputs with gradients recording) to the
-    CUDA training kernels.  Leave it off for the human trainer, whose loss differentiates through the sample
-    positions (not built: the reference torch path keeps serving it)."""
+def install(reference_root=None, train=False):
+    """train=True additionally routes the trainers' autograd path to the CUDA training kernels: Joiner.forward of
+    8x256 nets (gradients to the parameters and to input_pts / input_views, which is what
+    trainers/human_nerf_trainer.py:241-278 differentiates through) and raw2outputs with respect to `raw`
+    (trainers/vanilla_nerf_trainer.py:45-96).  Everything else of the training graph (warp, offset nets, SMPL,
+    regularisers) stays the reference's torch code."""
     if reference_root and reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     from . import autograd, ops, render
@@ -42,8 +43,8 @@ def install(reference_root=None, train_bkg=False):
     def joiner_forward(self, input_pts, input_views=None):
         if input_views is not None and on_cuda_nograd(input_pts, input_views) and self.nerf.use_viewdirs:
             return ops.joiner_forward(self, input_pts, input_views)
-        if (train_bkg and input_views is not None and torch.is_grad_enabled() and on_cuda(input_pts, input_views)
-                and trainable_arch(self) and not input_pts.requires_grad):
+        if (train and input_views is not None and torch.is_grad_enabled() and on_cuda(input_pts, input_views)
+                and trainable_arch(self)):
             return autograd.joiner_forward(self, input_pts, input_views)
         return ref_forward(self, input_pts, input_views)          # other training / CPU: reference torch path
     mv.Joiner.forward = joiner_forward
@@ -53,7 +54,8 @@ def install(reference_root=None, train_bkg=False):
     def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkg=True):
         if on_cuda_nograd(raw, z_vals, rays_d):
             return ops.raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkg)
-        if train_bkg and torch.is_grad_enabled() and on_cuda(raw, z_vals, rays_d) and not z_vals.requires_grad:
+        if (train and torch.is_grad_enabled() and on_cuda(raw, z_vals, rays_d)
+                and not z_vals.requires_grad and not rays_d.requires_grad):
             return autograd.raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkg)
         return ref_raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkg)
     ru.raw2outputs = raw2outputs

@@ -77,9 +77,11 @@ class Joiner(nn.Module):
 
     def forward(self, input_pts, input_views=None):
         """input_pts [...,3], input_views [...,3] -> [...,4] = (r,g,b,sigma). CUDA only.
-        Under autograd (any network parameter requiring grad) the training kernel runs and the result
-        carries gradients to the parameters (neuman_b200/autograd.py)."""
-        if torch.is_grad_enabled() and input_views is not None and any(p.requires_grad for p in self.nerf.parameters()):
+        Under autograd (a network parameter or an input requiring grad) the training kernel runs and the result
+        carries gradients to the parameters and to input_pts / input_views (neuman_b200/autograd.py)."""
+        if torch.is_grad_enabled() and input_views is not None and (
+                any(p.requires_grad for p in self.nerf.parameters())
+                or any(isinstance(t, torch.Tensor) and t.requires_grad for t in (input_pts, input_views))):
             from . import autograd
             return autograd.joiner_forward(self, input_pts, input_views)
         return ops.joiner_forward(self, input_pts, input_views)

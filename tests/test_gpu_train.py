@@ -91,6 +91,38 @@ def _reference_grads(joiner, pts, views, g, quant):
     return raw.detach(), {k[len('nerf.'):]: v.grad for k, v in net.sd.items()}
 
 
+@pytest.mark.parametrize("kind", ["posenc", "rotate"])
+def test_joiner_input_gradients(kind):
+    """dL/d(input_pts), dL/d(input_views) (what the human trainer's differentiable warp consumes,
+    trainers/human_nerf_trainer.py:266-276) against CPU autograd: fp16-operand emulation 3e-2, plain fp32 8e-2
+    (same mask-flip argument as for the parameters)."""
+    from tests.util import product_nets
+    coarse, fine, human = product_nets(DEV)
+    j = coarse if kind == "posenc" else human
+    n = 3000
+    torch.manual_seed(7)
+    pts0 = torch.randn(n, 3) * 0.7
+    views0 = torch.nn.functional.normalize(torch.randn(n, 3), dim=-1)
+    g = torch.randn(n, 4)
+    refs = []
+    for quant in (True, False):
+        p, v = pts0.clone().requires_grad_(True), views0.clone().requires_grad_(True)
+        _reference_grads(j, p, v, g, quant)
+        refs.append((p.grad, v.grad))
+    for frozen in (False, True):                    # inputs get gradients also when the net is frozen
+        for q in j.parameters():
+            q.requires_grad_(not frozen)
+        p, v = pts0.to(DEV).requires_grad_(True), views0.to(DEV).requires_grad_(True)
+        raw = j(p, v)
+        (raw * g.to(DEV)).sum().backward()
+        for got, rq, rf, name in ((p.grad.cpu(), refs[0][0], refs[1][0], "pts"), (v.grad.cpu(), refs[0][1], refs[1][1], "views")):
+            assert torch.isfinite(got).all()
+            assert _rel(got, rq) < 3e-2, (name, "vs emulation", _rel(got, rq))
+            assert _rel(got, rf) < 8e-2, (name, "vs fp32", _rel(got, rf))
+    for q in j.parameters():
+        q.requires_grad_(True)
+
+
 @pytest.mark.parametrize("kind,n", [("posenc", 1000), ("rotate", 4096 + 77), ("posenc", 256 * 148 * 2 + 300)])
 def test_joiner_backward(kind, n, monkeypatch):
     """Parameter gradients of Joiner.forward.
