@@ -111,6 +111,17 @@ int nm_mlp_backward(nm_ctx* ctx, int slot, const float* d_raw, const float* loss
 int nm_pe_backward(nm_ctx* ctx, int slot, int32_t which, const float* x, int64_t group, const float* d_enc,
                    int32_t ld, const float* inv_scale, int64_t n, float* d_x, void* stream);
 
+/* The nine 256-wide weight-gradient GEMMs of one backward pass, dW = G^T @ X with K = n (torch autograd's
+ * grad_output.t() @ input of nn.Linear), reading every fp16 plane once:
+ *   out[k], k = 0..6 : pts_linears.(k+1) w.r.t. its 256 hidden inputs = g_pre[k+1]^T @ stash_x[k]
+ *   out[7]           : feature_linear                                 = g_f^T @ stash_x[7]
+ *   out[8][:128]     : views_linears.0, feature columns               = g_v^T @ stash_f   (rows 128.. are zero)
+ * out: [9][256][256] fp32, overwritten; bias_out: [9][256] fp32, overwritten with the column sums of the item's
+ * g plane (= the bias gradients of pts_linears 1..7, feature_linear, views_linears.0[:128]); both carry the
+ * loss scale of the g planes. */
+int nm_dw_gemm(nm_ctx* ctx, const void* g_pre, const void* g_f, const void* g_v, const void* stash_x,
+               const void* stash_f, int64_t n, float* out, float* bias_out, void* stream);
+
 /* Bias gradients (the `.bias.grad` torch autograd accumulates): out[p][c] = sum_i src[p][i][c] over fp16 planes
  * src [planes][n][width] (width even, <= 256), fp32 accumulation.  out is overwritten. */
 int nm_colsum_f16(nm_ctx* ctx, const void* src, int32_t planes, int64_t n, int32_t width, float* out, void* stream);

@@ -154,11 +154,11 @@ def _colsum(ctx, t):
 
 
 def _weight_grads(joiner, stash, g, g_pre, g_f, g_v, inv):
-    """dW = g^T @ layer input (cuBLAS, K = n, fp16 operands / fp32 accumulate); g_* carry the loss scale 1/inv.
-    Every GEMM operand is a whole, 16-byte aligned stash plane (the 64-/32-channel encodings including their
-    padding, the [n,8]-padded dL/d raw), which keeps cuBLAS on its tensor-core kernels; the encodings' constant
-    1.0 channel returns the bias gradients of pts_linears.0/.5 and views_linears.0 as an extra GEMM column, the
-    other bias gradients are column sums (k_colsum_f16)."""
+    """dW = g^T @ layer input, K = n, fp16 operands / fp32 accumulate; g_* carry the loss scale 1/inv.
+    The nine 256-wide GEMMs and their bias gradients are one k_dw_gemm launch (csrc/dw_gemm.cu).  The narrow ones
+    (encodings, dL/d raw) go through cuBLAS with whole 16-byte aligned planes as operands (the 64-/32-channel
+    encodings including their padding, the [n,8]-padded dL/d raw: 63-/27-wide slices made cuBLAS fall back to an
+    sm_75 kernel); the position stash's constant-1.0 channel returns pts_linears.0's bias gradient as GEMM column 63."""
     sx, sf, sv, spe, sdpe, _ = stash
     ctx = _ctx_for(g)
     n_pe, n_dpe = joiner.pos_pe.out_dim, joiner.dir_pe.out_dim          # 63, 27: the 1.0 channel sits right after
@@ -172,21 +172,34 @@ def _weight_grads(joiner, stash, g, g_pre, g_f, g_v, inv):
     grads['alpha_linear.bias'] = g[:, 3].sum().reshape(1)
     gvt = g_v.t()
     wd = _mm32(gvt, sdpe) * inv                                           # [128, 32]
-    grads['views_linears.0.weight'] = torch.cat([_mm32(gvt, sf) * inv, wd[:, :n_dpe]], 1)
-    grads['views_linears.0.bias'] = wd[:, n_dpe]
-    grads['feature_linear.weight'] = _mm32(g_f.t(), sx[7]) * inv
-    grads['feature_linear.bias'] = _colsum(ctx, g_f[None])[0] * inv
-    db = _colsum(ctx, g_pre) * inv                                        # [8,256] (rows 0 and 5 also come from the GEMMs)
+    w0 = _mm32(g_pre[0].t(), spe) * inv                                   # [256,64]: column 63 = bias gradient (1.0 channel)
+    if os.environ.get("NEUMAN_DW_TORCH", "0") == "1":                     # cross-check path: cuBLAS GEMMs + column-sum kernel
+        dw = torch.zeros(9, 256, 256, device=g.device, dtype=torch.float32)
+        for k in range(7):
+            dw[k] = _mm32(g_pre[k + 1].t(), sx[k])
+        dw[7] = _mm32(g_f.t(), sx[7])
+        dw[8, :128] = _mm32(gvt, sf)
+        db = torch.zeros(9, 256, device=g.device, dtype=torch.float32)
+        db[:7] = _colsum(ctx, g_pre)[1:]
+        db[7] = _colsum(ctx, g_f[None])[0]
+        db[8, :128] = _colsum(ctx, g_v[None])[0]
+    else:                                                                 # k_dw_gemm: every plane read once at HBM rate
+        dw = torch.empty(9, 256, 256, device=g.device, dtype=torch.float32)
+        db = torch.empty(9, 256, device=g.device, dtype=torch.float32)
+        ctx.check(ctx.lib.nm_dw_gemm(ctx.h, _p(g_pre), _p(g_f), _p(g_v), _p(sx), _p(sf), g.shape[0], _p(dw), _p(db), _stream()))
+    dw, db = dw * inv, db * inv
+    grads['views_linears.0.weight'] = torch.cat([dw[8, :128], wd[:, :n_dpe]], 1)
+    grads['views_linears.0.bias'] = db[8, :128]
+    grads['feature_linear.weight'], grads['feature_linear.bias'] = dw[7], db[7]
     for l in range(8):
-        gt = g_pre[l].t()
         if l == 0:
-            w = _mm32(gt, spe)[:, :n_pe]
+            w = w0[:, :n_pe]
         elif l == 5:
-            w = torch.cat([_mm32(gt, spe)[:, :n_pe], _mm32(gt, sx[4])], 1)
+            w = torch.cat([_mm32(g_pre[5].t(), spe)[:, :n_pe] * inv, dw[4]], 1)
         else:
-            w = _mm32(gt, sx[l - 1])
-        grads['pts_linears.%d.weight' % l] = w * inv
-        grads['pts_linears.%d.bias' % l] = db[l]
+            w = dw[l - 1]
+        grads['pts_linears.%d.weight' % l] = w
+        grads['pts_linears.%d.bias' % l] = w0[:, n_pe] if l == 0 else db[l - 1]
     return grads
 
 

@@ -27,6 +27,7 @@ SOURCES = {           # file -> extra flags
     "mlp_simt.cu": [],
     "mlp_tc.cu": [],
     "mlp_tc_bwd.cu": [],
+    "dw_gemm.cu": [],
 }
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
           "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]

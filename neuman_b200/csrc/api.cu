@@ -339,6 +339,20 @@ extern "C" int nm_pe_backward(nm_ctx* ctx, int slot, int32_t which, const float*
   return nm_impl_pe_backward(ctx, net, which, x, group, d_enc, ld, inv_scale, n, d_x, (cudaStream_t)stream);
 }
 
+extern "C" int nm_dw_gemm(nm_ctx* ctx, const void* g_pre, const void* g_f, const void* g_v, const void* stash_x,
+                          const void* stash_f, int64_t n, float* out, float* bias_out, void* stream) {
+  if (!ctx) return NM_ERR_INVALID;
+  if (n < 0 || !out || !bias_out) NM_FAIL(ctx, NM_ERR_INVALID, "nm_dw_gemm: bad argument");
+  if (n == 0) {
+    NM_CHECK_CUDA(ctx, cudaMemsetAsync(out, 0, (size_t)9 * 256 * 256 * sizeof(float), (cudaStream_t)stream));
+    NM_CHECK_CUDA(ctx, cudaMemsetAsync(bias_out, 0, (size_t)9 * 256 * sizeof(float), (cudaStream_t)stream));
+    return NM_OK;
+  }
+  if (!g_pre || !g_f || !g_v || !stash_x || !stash_f) NM_FAIL(ctx, NM_ERR_INVALID, "nm_dw_gemm: null argument");
+  return nm_impl_dw_gemm(ctx, (const __half*)g_pre, (const __half*)g_f, (const __half*)g_v, (const __half*)stash_x,
+                         (const __half*)stash_f, n, out, bias_out, (cudaStream_t)stream);
+}
+
 extern "C" int nm_colsum_f16(nm_ctx* ctx, const void* src, int32_t planes, int64_t n, int32_t width, float* out, void* stream) {
   if (!ctx) return NM_ERR_INVALID;
   if (planes < 0 || n < 0 || width <= 0 || width > 256 || (width & 1)) NM_FAIL(ctx, NM_ERR_INVALID, "nm_colsum_f16: bad shape");

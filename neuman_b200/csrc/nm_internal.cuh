@@ -134,6 +134,8 @@ struct NmTrainStash {
 };
 int nm_impl_pe_backward(nm_ctx* ctx, const NmNet& net, int which, const float* x, int64_t group, const float* d_enc, int ld,
                         const float* inv_scale, int64_t n, float* d_x, cudaStream_t st);
+int nm_impl_dw_gemm(nm_ctx* ctx, const __half* g_pre, const __half* g_f, const __half* g_v, const __half* st_x,
+                    const __half* st_f, int64_t n, float* out, float* bias_out, cudaStream_t st);
 int nm_impl_colsum_f16(nm_ctx* ctx, const __half* src, int planes, int64_t n, int width, float* out, cudaStream_t st);
 int nm_tc_backward(nm_ctx* ctx, NmNet& net, const float* d_raw, const float* scale, int64_t n, const __half* st_v,
                    const uint32_t* st_m, __half* g_pre, __half* g_f, __half* g_v, cudaStream_t st);

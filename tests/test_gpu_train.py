@@ -52,6 +52,39 @@ def _rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-20))
 
 
+@pytest.mark.parametrize("n", [1, 63, 64, 1000, 4173, 64 * 74 * 3 + 5])
+def test_dw_gemm(n):
+    """k_dw_gemm (TMA-fed MN-major tcgen05 GEMMs, K = n) against fp32 matmuls of the same fp16 planes: fp32
+    accumulation in a different order -> 1e-4 relative L2; rows 128.. of the views item stay zero."""
+    from neuman_b200 import ops
+    from neuman_b200.ops import _p, _stream
+    torch.manual_seed(n)
+    g_pre = (torch.randn(8, n, 256, device=DEV) * 0.5).half()
+    g_f = (torch.randn(n, 256, device=DEV) * 0.5).half()
+    g_v = (torch.randn(n, 128, device=DEV) * 0.5).half()
+    sx = torch.relu(torch.randn(8, n, 256, device=DEV)).half()
+    sf = torch.randn(n, 256, device=DEV).half()
+    ctx = ops._ctx_for(g_f)
+    out = torch.full((9, 256, 256), float("nan"), device=DEV)
+    bias = torch.full((9, 256), float("nan"), device=DEV)
+    ctx.check(ctx.lib.nm_dw_gemm(ctx.h, _p(g_pre), _p(g_f), _p(g_v), _p(sx), _p(sf), n, _p(out), _p(bias), _stream()))
+    ref = torch.zeros(9, 256, 256, device=DEV)
+    for k in range(7):
+        ref[k] = g_pre[k + 1].float().t() @ sx[k].float()
+    ref[7] = g_f.float().t() @ sx[7].float()
+    ref[8, :128] = g_v.float().t() @ sf.float()
+    assert torch.isfinite(out).all()
+    assert torch.equal(out[8, 128:], torch.zeros_like(out[8, 128:]))
+    bref = torch.zeros(9, 256, device=DEV)
+    bref[:7] = g_pre[1:].float().sum(1)
+    bref[7] = g_f.float().sum(0)
+    bref[8, :128] = g_v.float().sum(0)
+    scale = float(bref.abs().max()) + 1.0
+    assert (bias - bref).abs().max() < 1e-4 * scale, (bias - bref).abs().max()
+    for k in range(9):
+        assert _rel(out[k].cpu(), ref[k].cpu()) < 2e-4, (k, _rel(out[k].cpu(), ref[k].cpu()))
+
+
 class _Q16(torch.autograd.Function):
     """round to fp16 in the forward, identity in the backward"""
     @staticmethod
@@ -143,6 +176,7 @@ def test_joiner_backward(kind, n, monkeypatch):
 
     def product(torch_chain):
         monkeypatch.setenv("NEUMAN_BWD_TORCH", "1" if torch_chain else "0")
+        monkeypatch.setenv("NEUMAN_DW_TORCH", "1" if torch_chain else "0")
         j.zero_grad()
         raw = j(pts.to(DEV), views.to(DEV))
         assert raw.requires_grad
