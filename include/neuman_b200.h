@@ -86,13 +86,18 @@ int nm_mlp_forward(nm_ctx* ctx, int slot, int mode, const float* pts, const floa
 /* Training forward of the same network (train.py -> trainers/*: Joiner.forward under autograd): as
  * nm_mlp_forward in NM_MLP_TC_F16 mode, and additionally writes the fp16 activations the backward
  * pass needs.  stash_x: [8][n][256] post-ReLU outputs of pts_linears 0..7; stash_f: [n][256]
- * feature_linear output; stash_v: [n][128] views_linears.0 post-ReLU; stash_pe: [n][64] encoded
- * position (channel 63 = 1.0); stash_dpe: [n][32] encoded direction (channel 27 = 1.0, 28.. zero): the
- * constant channel makes g^T @ stash deliver the bias gradient next to the weight gradient; stash_m:
- * [8][n][8] uint32 sign words, bit c of a 256-bit row = [output c of that pts_linears layer > 0]. */
+ * feature_linear output; stash_v: [n][128] views_linears.0 post-ReLU; stash_m: [8][n][8] uint32 ReLU sign
+ * words (16 bits per 16 outputs: bit j = [output 2j > 0], bit 8+j = [output 2j+1 > 0]). */
 int nm_mlp_forward_train(nm_ctx* ctx, int slot, const float* pts, const float* views, int64_t n,
                          int32_t views_per_ray, float* raw, void* stash_x, void* stash_f, void* stash_v,
-                         void* stash_pe, void* stash_dpe, void* stash_m, void* stream);
+                         void* stash_m, void* stream);
+
+/* Embedder.forward (models/vanilla.py:82-92) of net `slot` in the fp16 form the tensor-core kernels multiply with:
+ * which = 0: out [n][64] fp16 position encoding, channel 63 = 1.0; which = 1: out [n][32] direction encoding,
+ * channel 27 = 1.0, 28.. zero.  x: [n,3] (or [n/group,3] when group > 0).  The constant channel makes
+ * g^T @ out deliver the bias gradient next to the weight gradient of the layers that read the encoding. */
+int nm_encode_f16(nm_ctx* ctx, int slot, int32_t which, const float* x, int64_t group, int64_t n, void* out,
+                  void* stream);
 
 /* Adjoint of NeRF.forward (models/vanilla.py:120-152) with respect to the layer pre-activations
  * (what torch autograd computes inside loss.backward() for trainers/vanilla_nerf_trainer.py:222).

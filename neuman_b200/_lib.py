@@ -55,7 +55,8 @@ SIGNATURES = {
     "nm_launch_count": (_I64, [_P]),
     "nm_net_pack": (C.c_int, [_P, C.c_int, C.POINTER(NmNerfDesc), _P]),
     "nm_mlp_forward": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _I64, _I32, _P, _P]),
-    "nm_mlp_forward_train": (C.c_int, [_P, C.c_int, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nm_mlp_forward_train": (C.c_int, [_P, C.c_int, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P]),
+    "nm_encode_f16": (C.c_int, [_P, C.c_int, _I32, _P, _I64, _I64, _P, _P]),
     "nm_mlp_backward": (C.c_int, [_P, C.c_int, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "nm_pe_backward": (C.c_int, [_P, C.c_int, _I32, _P, _I64, _P, _I32, _P, _I64, _P, _P]),
     "nm_dw_gemm": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),

@@ -88,14 +88,14 @@ class _JoinerMLP(torch.autograd.Function):
         dev = pts.device
         h = dict(device=dev, dtype=torch.float16)
         sx, sf = torch.empty(8, n, 256, **h), torch.empty(n, 256, **h)
-        sv, spe, sdpe = torch.empty(n, 128, **h), torch.empty(n, 64, **h), torch.empty(n, 32, **h)
+        sv = torch.empty(n, 128, **h)
         sm = torch.empty(8, n, 8, device=dev, dtype=torch.int32)
         raw = torch.empty(n, 4, device=dev, dtype=torch.float32)
         if n:
             ctx.check(ctx.lib.nm_mlp_forward_train(ctx.h, slot, _p(pts), _p(views), n, 0, _p(raw), _p(sx), _p(sf), _p(sv),
-                                                   _p(spe), _p(sdpe), _p(sm), _stream()))
+                                                   _p(sm), _stream()))
         fctx.joiner = joiner
-        fctx.stash = (sx, sf, sv, spe, sdpe, sm)
+        fctx.stash = (sx, sf, sv, sm)
         fctx.save_for_backward(pts, views, *params)
         return raw
 
@@ -116,7 +116,7 @@ class _JoinerMLP(torch.autograd.Function):
         else:
             chain = _chain_torch if _use_torch_chain() else _chain_kernel
             g_pre, g_f, g_v, inv = chain(joiner, P, stash, g)
-            grads = _weight_grads(joiner, stash, g, g_pre, g_f, g_v, inv) if need_w else {}
+            grads = _weight_grads(joiner, stash, pts, views, g, g_pre, g_f, g_v, inv) if need_w else {}
             if fctx.needs_input_grad[0]:
                 d_pts = _input_grad(joiner, P, pts, 0, ((g_pre[0], 'pts_linears.0.weight', 0), (g_pre[5], 'pts_linears.5.weight', 0)), inv)
             if fctx.needs_input_grad[1]:
@@ -153,13 +153,26 @@ def _colsum(ctx, t):
     return out
 
 
-def _weight_grads(joiner, stash, g, g_pre, g_f, g_v, inv):
+def _encodings(joiner, pts, views):
+    """The fp16 encodings as the forward kernel multiplied them ([n,64] / [n,32], with their constant-1 channel)."""
+    ctx = _ctx_for(pts)
+    slot = ops.net_slot(joiner, ctx)
+    n = pts.shape[0]
+    spe = torch.empty(n, 64, device=pts.device, dtype=torch.float16)
+    sdpe = torch.empty(n, 32, device=pts.device, dtype=torch.float16)
+    ctx.check(ctx.lib.nm_encode_f16(ctx.h, slot, 0, _p(pts), 0, n, _p(spe), _stream()))
+    ctx.check(ctx.lib.nm_encode_f16(ctx.h, slot, 1, _p(views), 0, n, _p(sdpe), _stream()))
+    return spe, sdpe
+
+
+def _weight_grads(joiner, stash, pts, views, g, g_pre, g_f, g_v, inv):
     """dW = g^T @ layer input, K = n, fp16 operands / fp32 accumulate; g_* carry the loss scale 1/inv.
     The nine 256-wide GEMMs and their bias gradients are one k_dw_gemm launch (csrc/dw_gemm.cu).  The narrow ones
     (encodings, dL/d raw) go through cuBLAS with whole 16-byte aligned planes as operands (the 64-/32-channel
     encodings including their padding, the [n,8]-padded dL/d raw: 63-/27-wide slices made cuBLAS fall back to an
     sm_75 kernel); the position stash's constant-1.0 channel returns pts_linears.0's bias gradient as GEMM column 63."""
-    sx, sf, sv, spe, sdpe, _ = stash
+    sx, sf, sv, _ = stash
+    spe, sdpe = _encodings(joiner, pts, views)
     ctx = _ctx_for(g)
     n_pe, n_dpe = joiner.pos_pe.out_dim, joiner.dir_pe.out_dim          # 63, 27: the 1.0 channel sits right after
     grads = {}
@@ -204,7 +217,7 @@ def _weight_grads(joiner, stash, g, g_pre, g_f, g_v, inv):
 
 
 def _chain_kernel(joiner, P, stash, g):
-    sx, sf, sv, spe, sdpe, sm = stash
+    sx, sf, sv, sm = stash
     ctx = _ctx_for(g)
     slot = ops.net_slot(joiner, ctx)               # same weights as the forward: same slot (or an identical repack)
     n = g.shape[0]
@@ -219,7 +232,7 @@ def _chain_kernel(joiner, P, stash, g):
 def _chain_torch(joiner, P, stash, g):
     """The chain of k_mlp_tc_bwd restated with torch GEMMs on the same stash (same masks, same fp16 rounding
     points): the cross-check of the kernel in tests/test_gpu_train.py."""
-    sx, sf, sv, spe, sdpe, sm = stash
+    sx, sf, sv, sm = stash
     n_pe = joiner.pos_pe.out_dim
     scale = _pow2_scale(g, 256.0)
     inv = 1.0 / scale

@@ -300,15 +300,14 @@ extern "C" int nm_mlp_forward(nm_ctx* ctx, int slot, int mode, const float* pts,
 
 extern "C" int nm_mlp_forward_train(nm_ctx* ctx, int slot, const float* pts, const float* views, int64_t n,
                                     int32_t views_per_ray, float* raw, void* stash_x, void* stash_f, void* stash_v,
-                                    void* stash_pe, void* stash_dpe, void* stash_m, void* stream) {
+                                    void* stash_m, void* stream) {
   if (!ctx) return NM_ERR_INVALID;
   if (!pts || !views || views_per_ray < 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward_train: null pts/views");
-  if (!stash_x || !stash_f || !stash_v || !stash_pe || !stash_dpe || !stash_m)
+  if (!stash_x || !stash_f || !stash_v || !stash_m)
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward_train: null stash");
   if (views_per_ray > 0 && n % views_per_ray != 0)
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward_train: n is not a multiple of views_per_ray");
-  NmTrainStash sh{(__half*)stash_x, (__half*)stash_f, (__half*)stash_v, (__half*)stash_pe, (__half*)stash_dpe,
-                  (uint32_t*)stash_m};
+  NmTrainStash sh{(__half*)stash_x, (__half*)stash_f, (__half*)stash_v, (uint32_t*)stash_m};
   return mlp_dispatch(ctx, slot, NM_MLP_TC_F16, pts, views, nullptr, nullptr, nullptr, n, views_per_ray, raw, stream, &sh);
 }
 
@@ -323,6 +322,17 @@ extern "C" int nm_mlp_backward(nm_ctx* ctx, int slot, const float* d_raw, const 
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_backward: null argument");
   return nm_tc_backward(ctx, ctx->nets[slot], d_raw, loss_scale, n, (const __half*)stash_v, (const uint32_t*)stash_m,
                         (__half*)g_pre, (__half*)g_f, (__half*)g_v, (cudaStream_t)stream);
+}
+
+extern "C" int nm_encode_f16(nm_ctx* ctx, int slot, int32_t which, const float* x, int64_t group, int64_t n, void* out,
+                             void* stream) {
+  if (!ctx) return NM_ERR_INVALID;
+  if (slot < 0 || slot >= NM_MAX_NET_SLOTS || !ctx->nets[slot].packed)
+    NM_FAIL(ctx, NM_ERR_STATE, "nm_encode_f16: net slot not packed");
+  if ((which != 0 && which != 1) || n < 0 || group < 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_encode_f16: bad argument");
+  if (n == 0) return NM_OK;
+  if (!x || !out) NM_FAIL(ctx, NM_ERR_INVALID, "nm_encode_f16: null argument");
+  return nm_tc_encode(ctx, ctx->nets[slot], which, x, group, n, (__half*)out, (cudaStream_t)stream);
 }
 
 extern "C" int nm_pe_backward(nm_ctx* ctx, int slot, int32_t which, const float* x, int64_t group, const float* d_enc,

@@ -77,10 +77,9 @@ struct TcParams {
   __half* st_x;             // [8][n][256] post-ReLU outputs of layers 0..7
   __half* st_f;             // [n][256]    feature_linear output
   __half* st_v;             // [n][128]    views layer post-ReLU
-  __half* st_pe;            // [n][64]     position encoding (channel 63 = 1: bias column)
-  __half* st_dpe;           // [n][32]     direction encoding (channel 27 = 1: bias column, 28..31 = 0)
-  uint32_t* st_m;           // [8][n][8]   sign words: bit c of row = [layer output c > 0]
+  uint32_t* st_m;           // [8][n][8]   sign words, 16 bits per 16 columns: bit j = [col 2j > 0], bit 8+j = [col 2j+1 > 0]
   CUtensorMap map_x, map_f, map_v;   // TMA store maps of st_x / st_f / st_v (kTrain only)
+  int dbg;                  // debug (NEUMAN_TC_DEBUG): bit 0 = training kernel skips its TMA stash stores (timing experiments only)
   long long* trace;         // optional debug timeline (tools/tc_trace.py): [cta<2][role<2][event<4][256] clock64 stamps
 };
 
@@ -212,13 +211,13 @@ __device__ __forceinline__ uint32_t epi_sub16(const uint32_t (&v)[16], const flo
     *reinterpret_cast<uint4*>(grow + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     *reinterpret_cast<uint4*>(grow + c0 + 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
   }
-  uint32_t bits = 0;                            // bit c-c0 = [output > 0] (used by the training kernel only)
+  // ReLU sign word of these 16 outputs (training kernel only): bit j = [column c0+2j > 0], bit 8+j = [column
+  // c0+2j+1 > 0].  The outputs are non-negative f16, so adding 0x7fff to a half carries into its bit 15 exactly
+  // when it is non-zero; three integer ops per register.
+  uint32_t acc = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (packed[j] & 0x7fffu) bits |= 1u << (2 * j);
-    if (packed[j] & 0x7fff0000u) bits |= 1u << (2 * j + 1);
-  }
-  return bits;
+  for (int j = 0; j < 8; ++j) acc = (acc >> 1) | ((packed[j] + 0x7fff7fffu) & 0x80008000u);
+  return ((acc >> 8) & 0xffu) | ((acc >> 16) & 0xff00u);
 }
 
 // Drains `ncols` accumulator columns of this thread's TMEM lane into the activation block, software
@@ -433,13 +432,6 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
       float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
       if (tile_valid(round, g)) nm_fetch_sample(P.in, sample_index(round, g), p, v);
       encode_f16(P.pos_pe, p, pe_pos, 30);
-      if (kTrain && tile_valid(round, g)) {
-        uint4* dst = reinterpret_cast<uint4*>(P.st_pe + (size_t)sample_index(round, g) * 64);
-#pragma unroll
-        for (int j = 0; j < 7; ++j) dst[j] = make_uint4(pe_pos[4 * j], pe_pos[4 * j + 1], pe_pos[4 * j + 2], pe_pos[4 * j + 3]);
-        // the stash's padding channel 63 carries 1.0: g^T @ stash then yields the bias gradient as column 63
-        dst[7] = make_uint4(pe_pos[28], pe_pos[29], pe_pos[30], pe_pos[31] | 0x3C000000u);
-      }
     };
     auto encode_dir = [&](long long round) {
       float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
@@ -448,12 +440,6 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
       encode_f16(P.dir_pe, v, tmp, 12);
 #pragma unroll
       for (int j = 0; j < 16; ++j) pe_dir[j] = tmp[j];
-      if (kTrain && tile_valid(round, g)) {
-        uint4* dst = reinterpret_cast<uint4*>(P.st_dpe + (size_t)sample_index(round, g) * 32);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) dst[j] = make_uint4(pe_dir[4 * j], pe_dir[4 * j + 1], pe_dir[4 * j + 2], pe_dir[4 * j + 3]);
-        dst[3] = make_uint4(pe_dir[12], pe_dir[13] | 0x3C000000u, pe_dir[14], pe_dir[15]);      // channel 27 := 1.0 (bias column)
-      }
     };
     if (n_rounds > 0 && pe_owner) encode_pos(0);
     if (!kConst) {
@@ -500,26 +486,38 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
             if (s == 8 && g == t) { wait_pe_slot(round, 2, t); store_row_swizzled(pebuf, row, pe_dir, 4); }   // view dirs (:137)
             if (t == 0 && etid == 0) TC_TRACE(1, 1, nstep);
             if (kTrain) {
-              // activation stash: this warp's 32 rows x (128 | 64) columns, straight from the swizzled A buffer
-              fence_async_smem();
-              __syncwarp();
+              // activation stash: this warp's 32 rows x (128 | 64) columns leave by TMA straight from the swizzled
+              // A buffer.  Steps 0..7: the MMA thread is told first (the store and the next step's MMAs only read the
+              // slice).  Steps 8 and 9 hand the slice to another warp (the column split changes from 128 to 64 per
+              // warpgroup and back), so there the store must have finished reading before anyone goes on.
               const long long i0 = sample_index(round, t) - lane;            // first row of this warp
-              if (lane == 0 && i0 < P.in.n) {
-                const uint32_t src = sbase + C::OFF_ACT + t * 4 * TC_KB_BYTES + quad * 32 * 128;
-                if (s < 9) {
-                  const CUtensorMap* m = s < 8 ? &P.map_x : &P.map_f;
-                  tma_store_3d(m, src + (2 * g) * TC_KB_BYTES, 128 * g, (int)i0, s < 8 ? s : 0);
-                  tma_store_3d(m, src + (2 * g + 1) * TC_KB_BYTES, 128 * g + 64, (int)i0, s < 8 ? s : 0);
-                } else {
-                  tma_store_3d(&P.map_v, src + g * TC_KB_BYTES, 64 * g, (int)i0, 0);
+              const bool issue = lane == 0 && i0 < P.in.n && !(P.dbg & 1);
+              const uint32_t src = sbase + C::OFF_ACT + t * 4 * TC_KB_BYTES + quad * 32 * 128;
+              if (s < 8) {
+                publish(t);
+                if (issue) {
+                  tma_store_3d(&P.map_x, src + (2 * g) * TC_KB_BYTES, 128 * g, (int)i0, s);
+                  tma_store_3d(&P.map_x, src + (2 * g + 1) * TC_KB_BYTES, 128 * g + 64, (int)i0, s);
+                  tma_store_commit();
                 }
-                tma_store_commit();
-                // steps 8 and 9 hand this slice to another warp (the column split changes from 128 to 64 per
-                // warpgroup and back): the store must have finished reading before anyone is told to go on
-                if (s >= 8) tma_store_wait_read<0>();
+              } else {
+                fence_async_smem();
+                __syncwarp();
+                if (issue) {
+                  if (s == 8) {
+                    tma_store_3d(&P.map_f, src + (2 * g) * TC_KB_BYTES, 128 * g, (int)i0, 0);
+                    tma_store_3d(&P.map_f, src + (2 * g + 1) * TC_KB_BYTES, 128 * g + 64, (int)i0, 0);
+                  } else {
+                    tma_store_3d(&P.map_v, src + g * TC_KB_BYTES, 64 * g, (int)i0, 0);
+                  }
+                  tma_store_commit();
+                  tma_store_wait_read<0>();
+                }
+                publish(t);
               }
+            } else {
+              publish(t);
             }
-            publish(t);
             if (t == 0 && etid == 0) TC_TRACE(1, 2, nstep);
           } else {
             if (g == 0) {
@@ -620,6 +618,42 @@ __global__ void k_tc_bias(const float* b0, const float* b1, const float* b2, con
   out[11 * TC_BIAS_STRIDE + i] = alpha_w[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// The encodings as the tensor-core kernel feeds them to the MMAs (same code, same fp16 values), written out as
+// planes for the weight-gradient GEMMs of the training step: [n][64] (position, channel 63 = 1.0) or [n][32]
+// (direction, channel 27 = 1.0).  The constant channel multiplies a zero weight in the forward and returns the bias
+// gradient as an extra column of  g^T @ plane.  One thread per sample; 10-20 us per step, cheaper than stashing the
+// encodings from inside the MLP kernel (per-thread 128-byte rows from the epilogue warps: ~10 % of that kernel).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_encode_f16(NmPeSpec pe, int which, const float* __restrict__ x, long long group, long long n,
+                             __half* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long xi = group > 0 ? i / group : i;
+  const float xv[3] = {x[3 * xi], x[3 * xi + 1], x[3 * xi + 2]};
+  uint32_t e[32];
+  encode_f16(pe, xv, e, which == 0 ? 30 : 12);
+  if (which == 0) {
+    e[31] |= 0x3C000000u;                                                  // channel 63 := 1.0
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)i * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = make_uint4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+  } else {
+    e[13] |= 0x3C000000u;                                                  // channel 27 := 1.0
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)i * 32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+  }
+}
+
+int nm_tc_encode(nm_ctx* ctx, const NmNet& net, int which, const float* x, int64_t group, int64_t n, __half* out, cudaStream_t st) {
+  NmPeSpec pe = which == 0 ? NmPeSpec{net.desc.pos_pe_kind, net.desc.pos_n_freqs, net.f32 + net.o_pos_cyc}
+                           : NmPeSpec{net.desc.dir_pe_kind, net.desc.dir_n_freqs, net.f32 + net.o_dir_cyc};
+  k_encode_f16<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(pe, which, x, group, n, out);
+  NM_CHECK_LAUNCH(ctx);
+  return NM_OK;
+}
+
 static int tc_pair_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -715,8 +749,10 @@ int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* 
   P.raw = raw;
   P.n_tiles = (n + 128 * kpair - 1) / (128 * kpair);
   P.trace = nullptr;
+  P.dbg = 0;
+  if (const char* e = getenv("NEUMAN_TC_DEBUG")) P.dbg = atoi(e);
   P.st_x = stash ? stash->x : nullptr; P.st_f = stash ? stash->f : nullptr; P.st_v = stash ? stash->v : nullptr;
-  P.st_pe = stash ? stash->pe : nullptr; P.st_dpe = stash ? stash->dpe : nullptr; P.st_m = stash ? stash->m : nullptr;
+  P.st_m = stash ? stash->m : nullptr;
   memset(&P.map_x, 0, 3 * sizeof(CUtensorMap));
   if (stash) {
     if (n >= (int64_t)0x7fff0000) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward_train: n too large for one call");

@@ -56,21 +56,22 @@ struct BwParams {
 template <bool ALPHA, bool MASK, bool TO_ACT>
 __device__ __forceinline__ void bw_sub16(const uint32_t (&v)[16], int c0, float da, const float* s_walpha, uint32_t mbits,
                                          uint8_t* act, int row, __half* grow) {
+  float x[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    x[e] = __uint_as_float(v[e]);
+    if (ALPHA) x[e] = fmaf(da, s_walpha[c0 + e], x[e]);          // same address in every lane: a broadcast
+  }
+  if (MASK) {
+    // sign word layout (mlp_tc.cu epi_sub16): bit k < 8 = column 2k, bit 8+k = column 2k+1; tested in bit order so
+    // that the compiler moves them to predicates wholesale (R2P)
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (!((mbits >> k) & 1u)) x[k < 8 ? 2 * k : 2 * (k - 8) + 1] = 0.f;
+  }
   uint32_t packed[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
-    if (ALPHA) {
-      const float2 w = *reinterpret_cast<const float2*>(s_walpha + c0 + 2 * j);     // same address in every lane
-      x0 = fmaf(da, w.x, x0);
-      x1 = fmaf(da, w.y, x1);
-    }
-    if (MASK) {
-      if (!((mbits >> (2 * j)) & 1u)) x0 = 0.f;
-      if (!((mbits >> (2 * j + 1)) & 1u)) x1 = 0.f;
-    }
-    packed[j] = pack_f16x2(x0, x1, false);
-  }
+  for (int j = 0; j < 8; ++j) packed[j] = pack_f16x2(x[2 * j], x[2 * j + 1], false);
   if (TO_ACT) {
     uint8_t* blk = act + (c0 >> 6) * TC_KB_BYTES + row * 128;
     const int ch0 = (c0 & 63) >> 3;
@@ -314,20 +315,32 @@ __global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const _
           else if (b < BW_STEPS - 1) bw_step<false, true, true>(t_lane, g * 128, 0.f, s_walpha, mcur[t], act, row, grow);
           else bw_step<false, true, false>(t_lane, g * 128, 0.f, s_walpha, mcur[t], act, row, grow);
           if (b < BW_STEPS - 1) {
-            fence_async_smem();
-            __syncwarp();
             const long long i0 = sample_index(round, t) - lane;              // first row of this warp
-            if (lane == 0 && i0 < P.n) {
-              const uint32_t src = sbase + C::OFF_ACT + (t * 4 + 2 * g) * TC_KB_BYTES + quad * 32 * 128;
-              const CUtensorMap* m = b == 0 ? &P.map_f : &P.map_pre;
-              tma_store_3d(m, src, 128 * g, (int)i0, b == 0 ? 0 : 8 - b);
-              tma_store_3d(m, src + TC_KB_BYTES, 128 * g + 64, (int)i0, b == 0 ? 0 : 8 - b);
-              tma_store_commit();
+            const bool issue = lane == 0 && i0 < P.n;
+            const uint32_t src = sbase + C::OFF_ACT + (t * 4 + 2 * g) * TC_KB_BYTES + quad * 32 * 128;
+            const CUtensorMap* m = b == 0 ? &P.map_f : &P.map_pre;
+            const int plane = b == 0 ? 0 : 8 - b;
+            if (b < BW_STEPS - 2) {
+              // the MMA thread is told first: the store and the next step's MMAs only read this slice
+              publish(t);
+              if (issue) {
+                tma_store_3d(m, src, 128 * g, (int)i0, plane);
+                tma_store_3d(m, src + TC_KB_BYTES, 128 * g + 64, (int)i0, plane);
+                tma_store_commit();
+              }
+            } else {
               // after step 7 the tile's A buffer passes to the next round's head, written by the other
               // warpgroup: the store must have finished reading before anyone is told to go on
-              if (b == BW_STEPS - 2) tma_store_wait_read<0>();
+              fence_async_smem();
+              __syncwarp();
+              if (issue) {
+                tma_store_3d(m, src, 128 * g, (int)i0, plane);
+                tma_store_3d(m, src + TC_KB_BYTES, 128 * g + 64, (int)i0, plane);
+                tma_store_commit();
+                tma_store_wait_read<0>();
+              }
+              publish(t);
             }
-            publish(t);
           } else {
             tc_fence_before();
           }

@@ -128,12 +128,11 @@ struct NmTrainStash {
   __half* x;     // [8][n][256] post-ReLU outputs of pts_linears 0..7
   __half* f;     // [n][256]    feature_linear output
   __half* v;     // [n][128]    views layer post-ReLU
-  __half* pe;    // [n][64]     position encoding
-  __half* dpe;   // [n][32]     direction encoding
-  uint32_t* m;   // [8][n][8]   ReLU sign words of pts_linears 0..7 (bit c of the 256-bit row = [X > 0])
+  uint32_t* m;   // [8][n][8]   ReLU sign words of pts_linears 0..7 (16 bits per 16 columns, see mlp_tc.cu epi_sub16)
 };
 int nm_impl_pe_backward(nm_ctx* ctx, const NmNet& net, int which, const float* x, int64_t group, const float* d_enc, int ld,
                         const float* inv_scale, int64_t n, float* d_x, cudaStream_t st);
+int nm_tc_encode(nm_ctx* ctx, const NmNet& net, int which, const float* x, int64_t group, int64_t n, __half* out, cudaStream_t st);
 int nm_impl_dw_gemm(nm_ctx* ctx, const __half* g_pre, const __half* g_f, const __half* g_v, const __half* st_x,
                     const __half* st_f, int64_t n, float* out, float* bias_out, cudaStream_t st);
 int nm_impl_colsum_f16(nm_ctx* ctx, const __half* src, int planes, int64_t n, int width, float* out, cudaStream_t st);

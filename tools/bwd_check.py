@@ -20,9 +20,9 @@ cap = {}
 orig = nag._weight_grads
 
 
-def spy(joiner, stash, gg, g_pre, g_f, g_v, inv):
+def spy(joiner, stash, pts_, views_, gg, g_pre, g_f, g_v, inv):
     cap[os.environ["NEUMAN_BWD_TORCH"]] = (g_pre.float() * inv, g_f.float() * inv, g_v.float() * inv)
-    return orig(joiner, stash, gg, g_pre, g_f, g_v, inv)
+    return orig(joiner, stash, pts_, views_, gg, g_pre, g_f, g_v, inv)
 
 
 nag._weight_grads = spy

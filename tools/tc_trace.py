@@ -13,9 +13,17 @@ R, S = 32768, 128
 o = torch.randn(R, 3, device="cuda") * 0.3
 d = torch.nn.functional.normalize(torch.randn(R, 3, device="cuda"), dim=-1)
 z = torch.linspace(0, 3.14, S, device="cuda")[None].repeat(R, 1).contiguous()
-ops.mlp_forward_rays(coarse, o, d, z); torch.cuda.synchronize()
+TRAIN = len(sys.argv) > 1 and sys.argv[1] == "train"     # trace the training forward (activation stash) instead
+def run():
+    if TRAIN:
+        pts = (o[:, None] + d[:, None] * z[..., None]).reshape(-1, 3)
+        coarse(pts, d[:, None].expand(R, S, 3).reshape(-1, 3))
+    else:
+        ops.mlp_forward_rays(coarse, o, d, z)
+    torch.cuda.synchronize()
+run()
 buf.zero_()
-ops.mlp_forward_rays(coarse, o, d, z); torch.cuda.synchronize()
+run()
 t = buf.cpu().numpy().reshape(2, 2, 4, 256)
 m0, m1 = t[0, 0, 0], t[0, 0, 1]            # leader MMA thread: ready seen / issued+committed (tile 0)
 e0, e1, e2 = t[0, 1, 0], t[0, 1, 1], t[0, 1, 2]   # leader epilogue: acc ready / drained / published
