@@ -198,7 +198,8 @@ int nm_merge_samples(nm_ctx* ctx, int32_t n_lists, const float* const* z_lists,
 
 /* ---- observation -> canonical warp: utils/ray_utils.py:48-66 ------------------------------ */
 /* Per-frame mesh of one actor: verts [V,3] f32, faces [F,3] int32, T [>=V,4,4] f64 (HOST or DEVICE
- * pointers, flag `on_device`).  Builds the closest-point acceleration grid. */
+ * pointers, flag `on_device`).  Builds the closest-point BVH.  T may be NULL (n_T = 0) when only
+ * nm_signed_distance will query the mesh. */
 int nm_mesh_set(nm_ctx* ctx, int actor, const float* verts, int32_t n_verts, const int32_t* faces,
                 int32_t n_faces, const double* T, int32_t n_T, int32_t on_device, void* stream);
 /* pts [R,S,3] f32 -> can_pts, can_dirs [R,S,3] f32 (the reference's float64 results cast with
@@ -206,6 +207,12 @@ int nm_mesh_set(nm_ctx* ctx, int actor, const float* verts, int32_t n_verts, con
 int nm_warp_to_canonical(nm_ctx* ctx, int actor, const float* pts, int64_t R, int32_t S,
                          float* can_pts, float* can_dirs, float* closest, int32_t* face_id,
                          void* stream);
+
+/* igl.signed_distance(P, V, F) as the reference calls it (utils/ray_utils.py:70, trainers/human_nerf_trainer.py:310,
+ * 326) on the mesh of `actor`: S [n] f64 signed distance (pseudo-normal sign: negative inside), I [n] int32 closest
+ * face, C [n,3] f64 closest point; any of the three may be NULL.  pts: [n,3] f32. */
+int nm_signed_distance(nm_ctx* ctx, int actor, const float* pts, int64_t n, double* S, int32_t* I, double* C,
+                       void* stream);
 
 /* ---- SMPL per-vertex transforms: models/smpl.py:109-162,266-505; data_io/neuman_helper.py:299-330 ---- */
 typedef struct {

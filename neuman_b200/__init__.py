@@ -8,7 +8,8 @@ reference's own function / module signatures.  See DESIGN.md and INTEGRATION.md.
 from . import _lib
 from .models import Embedder, NeRF, Joiner, HumanNeRF, build_nerf, default_opt     # noqa: F401
 from .ops import (raw2outputs, ray_to_samples, ray_to_importance_samples, sample_pdf,          # noqa: F401
-                  geometry_guided_near_far, warp_samples_to_canonical, shot_rays, shot_all_rays,
+                  geometry_guided_near_far, warp_samples_to_canonical, warp_samples_to_canonical_diff, signed_distance,
+                  shot_rays, shot_all_rays,
                   joiner_forward, mlp_forward_rays, merge_samples, set_mesh)
 from .render import (render_vanilla, render_smpl_nerf, render_hybrid_nerf,                     # noqa: F401
                      render_hybrid_nerf_multi_persons, SimpleCapture)

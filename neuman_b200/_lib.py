@@ -71,6 +71,7 @@ SIGNATURES = {
     "nm_raw2outputs_backward": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _F, _I32, _P, _P, _P, _P, _P, _P]),
     "nm_merge_samples": (C.c_int, [_P, _I32, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I32), _I64, _P, _P, _P]),
     "nm_mesh_set": (C.c_int, [_P, C.c_int, _P, _I32, _P, _I32, _P, _I32, _I32, _P]),
+    "nm_signed_distance": (C.c_int, [_P, C.c_int, _P, _I64, _P, _P, _P, _P]),
     "nm_warp_to_canonical": (C.c_int, [_P, C.c_int, _P, _I64, _I32, _P, _P, _P, _P, _P]),
     "nm_smpl_vertex_transforms": (C.c_int, [_P, C.POINTER(NmSmplModel), _P, _P, _I32, _P, _P, _P]),
     "nm_smpl_scene_transforms": (C.c_int, [_P, C.POINTER(NmSmplModel), _P, _P, _P, C.POINTER(C.c_double), C.c_double,

@@ -40,6 +40,9 @@ static void free_mesh(NmMesh& m) {
   if (m.tri_sphere) cudaFree(m.tri_sphere);
   if (m.cell_start) cudaFree(m.cell_start);
   if (m.cell_tris) cudaFree(m.cell_tris);
+  if (m.vnorm) cudaFree(m.vnorm);
+  if (m.adj) cudaFree(m.adj);
+  if (m.pn_tmp) cudaFree(m.pn_tmp);
   m = NmMesh();
 }
 

@@ -52,6 +52,12 @@ struct NmMesh {
   float cell = 0.f;
   int3 dims = {0, 0, 0};
   size_t cap_refs = 0, cap_cells = 0, cap_verts = 0, cap_faces = 0, cap_T = 0;
+  // signed-distance support (warp.cu): angle-weighted vertex pseudo-normals, face across each edge; built on first use
+  bool has_T = false, pn_valid = false;
+  double* vnorm = nullptr;        // [V,3]
+  int32_t* adj = nullptr;         // [F,3]: face sharing edge (v0v1, v1v2, v2v0), -1 on a boundary
+  char* pn_tmp = nullptr;         // sort buffers of the adjacency build
+  size_t cap_vnorm = 0, cap_adj = 0, cap_pn_tmp = 0;
 };
 
 struct nm_ctx {

@@ -2,6 +2,8 @@
 // three per-vertex 4x4 transforms, inverse, apply; canonical view directions by finite differences.
 //
 //   nm_mesh_set            per-frame inputs of warp_samples_to_canonical (verts, faces, T) + LBVH build
+//   nm_signed_distance     <- igl.signed_distance as called by utils/ray_utils.py:70 (warp_samples_to_canonical_diff)
+//                             and trainers/human_nerf_trainer.py:310,326 (inside/outside of the SMPL surface)
 //   nm_warp_to_canonical   <- utils/ray_utils.py:48-66 (igl.point_mesh_squared_distance :53,
 //                             igl.barycentric_coordinates_tri :55, blend :56, inverse :57, apply :58,
 //                             finite-difference directions :62-64)
@@ -188,23 +190,14 @@ __device__ __forceinline__ float box_d2(const BvhView& B, int node, V3<float> p)
   return dx * dx + dy * dy + dz * dz;
 }
 
-__global__ void __launch_bounds__(128) k_warp_points(BvhView B, const float* __restrict__ verts,
-                                                      const int32_t* __restrict__ faces, const double* __restrict__ T,
-                                                      const float* __restrict__ pts, long long n,
-                                                      double* __restrict__ can64, float* __restrict__ closest_out,
-                                                      int32_t* __restrict__ face_out) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < n;
-  const long long ii = live ? i : n - 1;
-  V3<float> p{pts[3 * ii], pts[3 * ii + 1], pts[3 * ii + 2]};
+// Exact nearest-triangle search, one BVH traversal per WARP (packet traversal): the 32 lanes hold 32
+// consecutive samples (neighbours along a ray), a node is visited when ANY lane still needs it (its box is
+// not farther than that lane's best, 1e-5 slack keeps exact ties alive so the lowest face index wins them),
+// the nearer child is chosen by majority vote.  Control flow is warp-uniform; only the distances are per lane.
+// All 32 lanes must call it (dead lanes with a copy of a live point); `stack`: 64 ints of shared memory per warp.
+__device__ __forceinline__ int bvh_nearest_face(const BvhView& B, V3<float> p, int* stack) {
   float best = FLT_MAX;
   int best_f = 0x7fffffff;
-  // Exact nearest-triangle search, one BVH traversal per WARP (packet traversal): the 32 lanes hold 32
-  // consecutive samples (neighbours along a ray), a node is visited when ANY lane still needs it (its box is
-  // not farther than that lane's best, 1e-5 slack keeps exact ties alive so the lowest face index wins them),
-  // the nearer child is chosen by majority vote.  Control flow is warp-uniform; only the distances are per lane.
-  __shared__ int s_stack[4][64];
-  int* stack = s_stack[threadIdx.x >> 5];
   int sp = 0;
   int node = (B.n > 1) ? 0 : B.n - 1;
   while (true) {
@@ -242,6 +235,20 @@ __global__ void __launch_bounds__(128) k_warp_points(BvhView B, const float* __r
       if (!found) break;
     }
   }
+  return best_f;
+}
+
+__global__ void __launch_bounds__(128) k_warp_points(BvhView B, const float* __restrict__ verts,
+                                                      const int32_t* __restrict__ faces, const double* __restrict__ T,
+                                                      const float* __restrict__ pts, long long n,
+                                                      double* __restrict__ can64, float* __restrict__ closest_out,
+                                                      int32_t* __restrict__ face_out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  const long long ii = live ? i : n - 1;
+  V3<float> p{pts[3 * ii], pts[3 * ii + 1], pts[3 * ii + 2]};
+  __shared__ int s_stack[4][64];
+  const int best_f = bvh_nearest_face(B, p, s_stack[threadIdx.x >> 5]);
   if (!live) return;
   // ---- float64 re-evaluation on the winning triangle (utils/ray_utils.py:53-58) ----
   int i0 = faces[3 * best_f], i1 = faces[3 * best_f + 1], i2 = faces[3 * best_f + 2];
@@ -339,19 +346,22 @@ static BvhView bvh_view(const NmMesh& m) {
 extern "C" int nm_mesh_set(nm_ctx* ctx, int actor, const float* verts, int32_t n_verts, const int32_t* faces,
                            int32_t n_faces, const double* T, int32_t n_T, int32_t on_device, void* stream) {
   if (!ctx) return NM_ERR_INVALID;
-  if (actor < 0 || actor >= NM_MAX_ACTORS || !verts || !faces || !T || n_verts <= 0 || n_faces <= 0 || n_T < n_verts)
+  if (actor < 0 || actor >= NM_MAX_ACTORS || !verts || !faces || n_verts <= 0 || n_faces <= 0 || (T && n_T < n_verts))
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_mesh_set: bad argument (need n_T >= n_verts)");
+  if (!T) n_T = 0;                                   // distance queries only (nm_signed_distance)
   cudaStream_t st = (cudaStream_t)stream;
   NmMesh& m = ctx->meshes[actor];
   int rc;
   if ((rc = ensure(ctx, &m.verts, &m.cap_verts, (size_t)n_verts * 3))) return rc;
-  if ((rc = ensure(ctx, &m.T, &m.cap_T, (size_t)n_T * 16))) return rc;
+  if (T && (rc = ensure(ctx, &m.T, &m.cap_T, (size_t)n_T * 16))) return rc;
   if ((rc = ensure(ctx, &m.faces, &m.cap_faces, (size_t)n_faces * 3))) return rc;
   cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   NM_CHECK_CUDA(ctx, cudaMemcpyAsync(m.verts, verts, (size_t)n_verts * 3 * sizeof(float), kind, st));
   NM_CHECK_CUDA(ctx, cudaMemcpyAsync(m.faces, faces, (size_t)n_faces * 3 * sizeof(int32_t), kind, st));
-  NM_CHECK_CUDA(ctx, cudaMemcpyAsync(m.T, T, (size_t)n_T * 16 * sizeof(double), kind, st));
+  if (T) NM_CHECK_CUDA(ctx, cudaMemcpyAsync(m.T, T, (size_t)n_T * 16 * sizeof(double), kind, st));
   m.n_verts = n_verts; m.n_faces = n_faces; m.n_T = n_T;
+  m.has_T = T != nullptr;
+  m.pn_valid = false;
   // bounding box on the host (82 KB; once per frame) -- only used to normalise the Morton codes
   std::vector<float> hv((size_t)n_verts * 3);
   if (on_device) {
@@ -399,7 +409,8 @@ extern "C" int nm_warp_to_canonical(nm_ctx* ctx, int actor, const float* pts, in
                                     float* can_dirs, float* closest, int32_t* face_id, void* stream) {
   if (!ctx) return NM_ERR_INVALID;
   if (R == 0) return NM_OK;
-  if (actor < 0 || actor >= NM_MAX_ACTORS || !ctx->meshes[actor].set) NM_FAIL(ctx, NM_ERR_STATE, "nm_warp_to_canonical: mesh not set");
+  if (actor < 0 || actor >= NM_MAX_ACTORS || !ctx->meshes[actor].set || !ctx->meshes[actor].has_T)
+    NM_FAIL(ctx, NM_ERR_STATE, "nm_warp_to_canonical: mesh (with per-vertex transforms) not set");
   if (!pts || !can_pts || R < 0 || S <= 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_warp_to_canonical: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   NmMesh& m = ctx->meshes[actor];
@@ -416,6 +427,142 @@ extern "C" int nm_warp_to_canonical(nm_ctx* ctx, int actor, const float* pts, in
   k_warp_points<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, m.verts, m.faces, m.T, pts, n, can64, closest, face_id);
   NM_CHECK_LAUNCH(ctx);
   k_warp_dirs<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(can64, R, S, can_pts, can_dirs);
+  NM_CHECK_LAUNCH(ctx);
+  return NM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Signed distance to the mesh (igl.signed_distance, pseudo-normal sign): closest point and face as above, sign of
+// (p - closest) . N with N = the face normal, or the sum of the two unit face normals at an edge, or the
+// angle-weighted vertex normal, according to which barycentric coordinates of the closest point vanish
+// (Baerentzen & Aanaes 2005, what igl::pseudonormal_test evaluates).  float64 after the fp32 arg-min.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ V3<double> ld3d(const float* v, int i) { return {(double)v[3 * i], (double)v[3 * i + 1], (double)v[3 * i + 2]}; }
+__device__ __forceinline__ V3<double> unit_normal(V3<double> a, V3<double> b, V3<double> c) {
+  V3<double> n = cross(sub(b, a), sub(c, a));
+  const double l = sqrt(dot(n, n));
+  const double s = 1.0 / fmax(l, 1e-300);
+  return {n.x * s, n.y * s, n.z * s};
+}
+__device__ __forceinline__ double corner_angle(V3<double> u, V3<double> v) {
+  const double c = dot(u, v) / fmax(sqrt(dot(u, u)) * sqrt(dot(v, v)), 1e-300);
+  return acos(fmin(1.0, fmax(-1.0, c)));
+}
+
+__global__ void k_vertex_normals(const float* __restrict__ verts, const int32_t* __restrict__ faces, int nf, double* __restrict__ vnorm) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  const int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
+  const V3<double> A = ld3d(verts, i0), B = ld3d(verts, i1), C = ld3d(verts, i2);
+  const V3<double> n = unit_normal(A, B, C);
+  const double w0 = corner_angle(sub(B, A), sub(C, A)), w1 = corner_angle(sub(C, B), sub(A, B)), w2 = corner_angle(sub(A, C), sub(B, C));
+  atomicAdd(vnorm + 3 * i0, n.x * w0); atomicAdd(vnorm + 3 * i0 + 1, n.y * w0); atomicAdd(vnorm + 3 * i0 + 2, n.z * w0);
+  atomicAdd(vnorm + 3 * i1, n.x * w1); atomicAdd(vnorm + 3 * i1 + 1, n.y * w1); atomicAdd(vnorm + 3 * i1 + 2, n.z * w1);
+  atomicAdd(vnorm + 3 * i2, n.x * w2); atomicAdd(vnorm + 3 * i2 + 1, n.y * w2); atomicAdd(vnorm + 3 * i2 + 2, n.z * w2);
+}
+
+// edge e of face f joins vertices (e, e+1 mod 3); key = (min << 32) | max, value = 3f + e
+__global__ void k_edge_keys(const int32_t* __restrict__ faces, int nf, unsigned long long* __restrict__ keys, int32_t* __restrict__ vals) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= 3 * nf) return;
+  const int f = q / 3, e = q - 3 * f;
+  const unsigned a = (unsigned)faces[3 * f + e], b = (unsigned)faces[3 * f + (e + 1) % 3];
+  keys[q] = ((unsigned long long)min(a, b) << 32) | (unsigned long long)max(a, b);
+  vals[q] = q;
+}
+__global__ void k_edge_adjacency(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, int ne, int32_t* __restrict__ adj) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= ne) return;
+  int other = -1;
+  if (q + 1 < ne && keys[q + 1] == keys[q]) other = vals[q + 1] / 3;
+  else if (q > 0 && keys[q - 1] == keys[q]) other = vals[q - 1] / 3;
+  adj[vals[q]] = other;
+}
+
+__global__ void __launch_bounds__(128) k_signed_distance(BvhView B, const float* __restrict__ verts, const int32_t* __restrict__ faces,
+                                                          const double* __restrict__ vnorm, const int32_t* __restrict__ adj,
+                                                          const float* __restrict__ pts, long long n, double* __restrict__ S_out,
+                                                          int32_t* __restrict__ I_out, double* __restrict__ C_out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  const long long ii = live ? i : n - 1;
+  V3<float> p{pts[3 * ii], pts[3 * ii + 1], pts[3 * ii + 2]};
+  __shared__ int s_stack[4][64];
+  const int f = bvh_nearest_face(B, p, s_stack[threadIdx.x >> 5]);
+  if (!live) return;
+  const int iv[3] = {faces[3 * f], faces[3 * f + 1], faces[3 * f + 2]};
+  const V3<double> P{(double)p.x, (double)p.y, (double)p.z};
+  const V3<double> A = ld3d(verts, iv[0]), Bv = ld3d(verts, iv[1]), C = ld3d(verts, iv[2]);
+  const V3<double> Q = closest_on_tri<double>(P, A, Bv, C);
+  const V3<double> nrm = cross(sub(Bv, A), sub(C, A));
+  const double nn = dot(nrm, nrm);
+  double L[3];
+  L[0] = dot(nrm, cross(sub(C, Bv), sub(Q, Bv))) / nn;
+  L[1] = dot(nrm, cross(sub(A, C), sub(Q, C))) / nn;
+  L[2] = 1.0 - L[0] - L[1];
+  const double eps = 1e-9;
+  const bool on[3] = {L[0] > eps, L[1] > eps, L[2] > eps};
+  const int cnt = (int)on[0] + (int)on[1] + (int)on[2];
+  V3<double> N = unit_normal(A, Bv, C);
+  if (cnt == 1) {
+    const int k = L[0] >= L[1] ? (L[0] >= L[2] ? 0 : 2) : (L[1] >= L[2] ? 1 : 2);
+    N = {vnorm[3 * iv[k]], vnorm[3 * iv[k] + 1], vnorm[3 * iv[k] + 2]};
+  } else if (cnt == 2) {
+    const int e = !on[2] ? 0 : (!on[0] ? 1 : 2);          // edge (v0v1), (v1v2), (v2v0)
+    const int g = adj[3 * f + e];
+    if (g >= 0) {
+      const V3<double> M = unit_normal(ld3d(verts, faces[3 * g]), ld3d(verts, faces[3 * g + 1]), ld3d(verts, faces[3 * g + 2]));
+      N = {N.x + M.x, N.y + M.y, N.z + M.z};
+    }
+  }
+  const V3<double> d = sub(P, Q);
+  const double s = dot(d, N);
+  const double dist = sqrt(dot(d, d));
+  if (S_out) S_out[i] = s < 0.0 ? -dist : dist;
+  if (I_out) I_out[i] = f;
+  if (C_out) { C_out[3 * i] = Q.x; C_out[3 * i + 1] = Q.y; C_out[3 * i + 2] = Q.z; }
+}
+
+static int build_pseudonormals(nm_ctx* ctx, NmMesh& m, cudaStream_t st) {
+  int rc;
+  const int nf = m.n_faces, ne = 3 * nf;
+  if ((rc = ensure(ctx, &m.vnorm, &m.cap_vnorm, (size_t)m.n_verts * 3))) return rc;
+  if ((rc = ensure(ctx, &m.adj, &m.cap_adj, (size_t)ne))) return rc;
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, ne);
+  const size_t kb = ((size_t)ne * 8 + 255) & ~size_t(255), vb = ((size_t)ne * 4 + 255) & ~size_t(255);
+  if ((rc = ensure(ctx, &m.pn_tmp, &m.cap_pn_tmp, 2 * kb + 2 * vb + cub_bytes + 256))) return rc;
+  auto* k_in = reinterpret_cast<unsigned long long*>(m.pn_tmp);
+  auto* k_out = reinterpret_cast<unsigned long long*>(m.pn_tmp + kb);
+  auto* v_in = reinterpret_cast<int32_t*>(m.pn_tmp + 2 * kb);
+  auto* v_out = reinterpret_cast<int32_t*>(m.pn_tmp + 2 * kb + vb);
+  char* tmp = m.pn_tmp + 2 * kb + 2 * vb;
+  NM_CHECK_CUDA(ctx, cudaMemsetAsync(m.vnorm, 0, (size_t)m.n_verts * 3 * sizeof(double), st));
+  k_vertex_normals<<<(nf + 127) / 128, 128, 0, st>>>(m.verts, m.faces, nf, m.vnorm);
+  NM_CHECK_LAUNCH(ctx);
+  k_edge_keys<<<(ne + 127) / 128, 128, 0, st>>>(m.faces, nf, k_in, v_in);
+  NM_CHECK_LAUNCH(ctx);
+  NM_CHECK_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp, cub_bytes, k_in, k_out, v_in, v_out, ne, 0, 64, st));
+  NM_LAUNCHED(ctx);
+  k_edge_adjacency<<<(ne + 127) / 128, 128, 0, st>>>(k_out, v_out, ne, m.adj);
+  NM_CHECK_LAUNCH(ctx);
+  m.pn_valid = true;
+  return NM_OK;
+}
+
+extern "C" int nm_signed_distance(nm_ctx* ctx, int actor, const float* pts, int64_t n, double* S, int32_t* I, double* C, void* stream) {
+  if (!ctx) return NM_ERR_INVALID;
+  if (n == 0) return NM_OK;
+  if (actor < 0 || actor >= NM_MAX_ACTORS || !ctx->meshes[actor].set) NM_FAIL(ctx, NM_ERR_STATE, "nm_signed_distance: mesh not set");
+  if (!pts || n < 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_signed_distance: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  NmMesh& m = ctx->meshes[actor];
+  if (!m.pn_valid) {
+    int rc = build_pseudonormals(ctx, m, st);
+    if (rc != NM_OK) return rc;
+  }
+  k_signed_distance<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(bvh_view(m), m.verts, m.faces, m.vnorm, m.adj, pts, n, S, I, C);
   NM_CHECK_LAUNCH(ctx);
   return NM_OK;
 }

@@ -77,21 +77,45 @@ def install(reference_root=None, train=False):
 
     ref_rts, ref_rtis, ref_pdf = ry.ray_to_samples, ry.ray_to_importance_samples, ry.sample_pdf
 
+    def no_grad_inputs(*ts):
+        return on_cuda(*ts) and (not torch.is_grad_enabled() or train)
+
     def ray_to_samples(ray_batch, samples_per_ray, lindisp=False, perturb=0., device='cpu', append_t=None):
-        if append_t is None and on_cuda_nograd(ray_batch['origin'], ray_batch['near']):
+        if append_t is None and no_grad_inputs(ray_batch['origin'], ray_batch['near']):
             return ops.ray_to_samples(ray_batch, samples_per_ray, lindisp, perturb)
         return ref_rts(ray_batch, samples_per_ray, lindisp, perturb, device, append_t)
 
     def ray_to_importance_samples(ray_batch, z_vals, weights, importance_samples_per_ray, device='cpu',
                                   including_old=True, append_t=None):
-        if append_t is None and on_cuda_nograd(z_vals, weights):
+        if append_t is None and no_grad_inputs(z_vals, weights):       # samples are constants of the step (:150 detaches)
             return ops.ray_to_importance_samples(ray_batch, z_vals, weights, importance_samples_per_ray,
                                                  including_old=including_old)
         return ref_rtis(ray_batch, z_vals, weights, importance_samples_per_ray, device, including_old, append_t)
 
     def sample_pdf(bins, weights, N_samples, det=False, device='cpu'):
-        if on_cuda_nograd(bins, weights):
+        if no_grad_inputs(bins, weights):
             return ops.sample_pdf(bins, weights, N_samples, det)
         return ref_pdf(bins, weights, N_samples, det, device)
     ry.ray_to_samples, ry.ray_to_importance_samples, ry.sample_pdf = ray_to_samples, ray_to_importance_samples, sample_pdf
+    if train:
+        # the human trainer's CPU libigl queries (utils/ray_utils.py:70, trainers/human_nerf_trainer.py:310,326)
+        ref_diff = ry.warp_samples_to_canonical_diff
+
+        def warp_samples_to_canonical_diff(pts, verts, faces, T):
+            if isinstance(verts, torch.Tensor) and verts.is_cuda and isinstance(T, torch.Tensor) and T.is_cuda:
+                T_inv, f_id, sd = ops.warp_samples_to_canonical_diff(pts, verts, faces, T)
+                return T_inv, f_id.cpu().numpy(), sd.cpu().numpy()        # the reference returns igl's numpy arrays
+            return ref_diff(pts, verts, faces, T)
+        ry.warp_samples_to_canonical_diff = warp_samples_to_canonical_diff
+        try:
+            igl = importlib.import_module("igl")
+            ref_sd = igl.signed_distance
+
+            def signed_distance(P, V, F, *a, **k):
+                if a or k or not torch.cuda.is_available():
+                    return ref_sd(P, V, F, *a, **k)
+                return ops.signed_distance(P, V, F)
+            igl.signed_distance = signed_distance
+        except ImportError:
+            pass
     return {"render_utils": ru, "ray_utils": ry, "vanilla": mv}

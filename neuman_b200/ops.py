@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import Context, NmCamera, NmNerfDesc
+from ._lib import Context, NmCamera, NmNerfDesc, NM_MAX_ACTORS
 
 DEFAULT_GEO_THRESH = 0.2     # utils/constant.py:14
 
@@ -284,18 +284,82 @@ def merge_samples(z_list, raw_list):
 # observation -> canonical warp
 # ---------------------------------------------------------------------------------------------
 def set_mesh(verts, faces, T, actor=0, device=None):
-    """Uploads one actor's per-frame mesh (verts [V,3], faces [F,>=3], T [>=V,4,4]) and builds the grid."""
+    """Uploads one actor's per-frame mesh (verts [V,3], faces [F,>=3], T [>=V,4,4] or None) and builds the BVH.
+    CUDA tensors are taken from device memory, anything else goes through host arrays."""
+    if isinstance(verts, torch.Tensor) and verts.is_cuda:
+        device = verts.device
+        ctx = Context.get(device.index if device.index is not None else torch.cuda.current_device())
+        v = verts.detach().float().contiguous()
+        if isinstance(faces, torch.Tensor):
+            f = faces.detach()[:, :3].to(device=device, dtype=torch.int32).contiguous()
+        else:
+            f = torch.from_numpy(np.ascontiguousarray(np.asarray(faces)[:, :3], dtype=np.int32)).to(device)
+        t = None
+        if T is not None:
+            t = (T.detach() if isinstance(T, torch.Tensor) else torch.as_tensor(np.asarray(T))).to(device=device, dtype=torch.float64)
+            t = t.contiguous().reshape(-1, 16)
+        with torch.cuda.device(device):
+            ctx.check(ctx.lib.nm_mesh_set(ctx.h, int(actor), _p(v), v.shape[0], _p(f), f.shape[0], _p(t),
+                                          0 if t is None else t.shape[0], 1, _stream()))
+        return ctx
     device = torch.device(device or "cuda")
     ctx = Context.get(device.index if device.index is not None else torch.cuda.current_device())
     v = np.ascontiguousarray(verts.detach().cpu().numpy() if isinstance(verts, torch.Tensor) else verts, dtype=np.float32)
     f = np.ascontiguousarray(np.asarray(faces)[:, :3], dtype=np.int32)
-    t = np.ascontiguousarray(T.detach().cpu().numpy() if isinstance(T, torch.Tensor) else T, dtype=np.float64)
-    t = t.reshape(-1, 16)
+    tp, tn = None, 0
+    if T is not None:
+        t = np.ascontiguousarray(T.detach().cpu().numpy() if isinstance(T, torch.Tensor) else T, dtype=np.float64)
+        t = t.reshape(-1, 16)
+        tp, tn = t.ctypes.data_as(C.c_void_p), t.shape[0]
     with torch.cuda.device(device):
         ctx.check(ctx.lib.nm_mesh_set(ctx.h, int(actor), v.ctypes.data_as(C.c_void_p), v.shape[0],
-                                      f.ctypes.data_as(C.c_void_p), f.shape[0], t.ctypes.data_as(C.c_void_p),
-                                      t.shape[0], 0, _stream()))
+                                      f.ctypes.data_as(C.c_void_p), f.shape[0], tp, tn, 0, _stream()))
     return ctx
+
+
+def signed_distance(pts, verts, faces, actor=NM_MAX_ACTORS - 1, device=None):
+    """igl.signed_distance(P, V, F) as the reference calls it (utils/ray_utils.py:70,
+    trainers/human_nerf_trainer.py:310,326): (S [n] signed distance, negative inside; I [n] closest face;
+    C [n,3] closest point).  numpy in -> float64 / int32 numpy out (igl's types); CUDA tensors in -> CUDA tensors out
+    (float64, int32, float64).  Uses the last actor slot by default so that the renderers' meshes stay set."""
+    as_numpy = not isinstance(pts, torch.Tensor)
+    if isinstance(verts, torch.Tensor) and verts.is_cuda:
+        device = verts.device
+    device = torch.device(device or (pts.device if isinstance(pts, torch.Tensor) and pts.is_cuda else "cuda"))
+    if isinstance(verts, torch.Tensor) and not verts.is_cuda:
+        verts = verts.detach().to(device)
+    ctx = set_mesh(verts, faces, None, actor, device)
+    p = _f32(pts, device).reshape(-1, 3)
+    n = p.shape[0]
+    S = torch.empty(n, device=p.device, dtype=torch.float64)
+    I = torch.empty(n, device=p.device, dtype=torch.int32)
+    Cl = torch.empty(n, 3, device=p.device, dtype=torch.float64)
+    with torch.cuda.device(p.device):
+        ctx.check(ctx.lib.nm_signed_distance(ctx.h, int(actor), _p(p), n, _p(S), _p(I), _p(Cl), _stream()))
+    if as_numpy:
+        return S.cpu().numpy(), I.cpu().numpy(), Cl.cpu().numpy()
+    return S, I, Cl
+
+
+def warp_samples_to_canonical_diff(pts, verts, faces, T, actor=NM_MAX_ACTORS - 1):
+    """utils/ray_utils.py:69-93: the closest-face query (igl.signed_distance on the CPU in the reference, :70) runs on
+    the device; the differentiable part -- barycentric coordinates of the closest point from cross products (:72-88),
+    blend of the three per-vertex transforms and its inverse (:90-91) -- is the same torch algebra, so gradients reach
+    `verts` and `T` through autograd exactly as in the reference.  pts: [n,3] numpy or tensor (treated as constants);
+    verts [V,3], T [V,4,4]: CUDA tensors.  Returns (T_interp_inv [n,4,4], f_id [n], signed_dist [n])."""
+    signed_dist, f_id, closest = signed_distance(torch.as_tensor(np.asarray(pts)) if not isinstance(pts, torch.Tensor) else pts.detach(),
+                                                 verts, faces, actor=actor, device=verts.device)
+    fa = (faces if isinstance(faces, torch.Tensor) else torch.as_tensor(np.asarray(faces)))[:, :3].to(verts.device).long()
+    tri = verts[fa[f_id.long()]]                                        # [n,3,3]
+    closest = closest.float()
+    a, b, c = tri[:, 0], tri[:, 1], tri[:, 2]
+    nrm = torch.cross(b - a, c - a, dim=-1)
+    denom = (nrm * nrm).sum(-1)
+    u = (nrm * torch.cross(c - b, closest - b, dim=-1)).sum(-1) / denom
+    v = (nrm * torch.cross(a - c, closest - c, dim=-1)).sum(-1) / denom
+    bary = torch.stack([u, v, 1 - u - v], dim=1)
+    T_interp = (T[fa[f_id.long()]] * bary[..., None, None]).sum(dim=1)
+    return torch.inverse(T_interp), f_id, signed_dist
 
 
 def warp_samples_to_canonical(pts, verts, faces, T, actor=0, return_face_id=False):
