@@ -152,7 +152,12 @@ def shot_rays(cap, xys, device=None):
     """utils/ray_utils.py:23-29 -> (origins, dirs) float32 CUDA tensors [n,3]."""
     device = torch.device(device or "cuda")
     ctx = Context.get(device.index if device.index is not None else torch.cuda.current_device())
-    xy = torch.as_tensor(np.ascontiguousarray(np.asarray(xys)[:, :2]).astype(np.int32)).to(device)
+    if isinstance(xys, torch.Tensor) and xys.is_cuda:           # already on the device (neuman_b200/data.py)
+        device = xys.device
+        ctx = Context.get(device.index if device.index is not None else torch.cuda.current_device())
+        xy = xys[:, :2].to(torch.int32).contiguous()
+    else:
+        xy = torch.as_tensor(np.ascontiguousarray(np.asarray(xys)[:, :2]).astype(np.int32)).to(device)
     n = xy.shape[0]
     o = torch.empty(n, 3, device=device)
     d = torch.empty(n, 3, device=device)

@@ -259,3 +259,139 @@ def test_vanilla_train_step_matches_autograd():
         last = float(nt.train_batch(coarse, fine, optim, batch, opt, iteration=it, **kw))
         first = last if first is None else first
     assert np.isfinite(last) and last < first, (first, last)
+
+
+def test_background_ray_batcher():
+    """neuman_b200.data.BackgroundRayBatcher against a numpy restatement of BackgroundRayDataset.__getitem__
+    (datasets/background_rays.py:56-139) on the same pixels (rays: oracle shot_rays), bit-exact except the rays
+    (2e-6, as in test_gpu_stages); the random part only draws admissible pixels and fills the batch."""
+    import types
+    import neuman_b200 as nb
+    from neuman_b200 import data as nd
+    from neuman_b200.render import SimpleCapture
+    rng = np.random.RandomState(3)
+    caps = []
+    for k in range(3):
+        H, W = 48 + 8 * k, 64
+        K = np.array([[60.0, 0, W / 2], [0, 60.0, H / 2], [0, 0, 1]])
+        c2w = np.eye(4)
+        c2w[:3, 3] = rng.normal(0, 0.2, 3)
+        cap = SimpleCapture(K, c2w, H, W, near=0.3 + 0.1 * k, far=4.0 + k)
+        cap.image = rng.randint(0, 256, (H, W, 3)).astype(np.uint8)
+        cap.depth_map = rng.uniform(0.5, 3.0, (H, W)).astype(np.float32)
+        cap.mask = (rng.uniform(size=(H, W)) < 0.3).astype(np.uint8)
+        cap.binary_mask = cap.mask
+        if k == 1:
+            cap.border_mask = (rng.uniform(size=(H, W)) < 0.2).astype(np.uint8)
+        cap.frame_id = {'frame_id': k, 'total_frames': 7}
+        caps.append(cap)
+    opt = types.SimpleNamespace(rays_per_batch=500, use_fused_depth=False, ablate_nerft=False)
+    b = nd.BackgroundRayBatcher(opt, caps)
+    np.random.seed(0)
+    coords = b.sample_coords()
+    assert sum(0 if c is None else c.shape[0] for c in coords) == 500
+    for cap, c in zip(caps, coords):
+        if c is None:
+            continue
+        c = c.cpu().numpy()
+        bad = cap.mask[c[:, 1], c[:, 0]] != 0
+        if hasattr(cap, 'border_mask'):
+            bad |= cap.border_mask[c[:, 1], c[:, 0]] != 0
+        assert not bad.any()
+    out = b.batch_from_coords(coords)
+    ref = {k: [] for k in ('color', 'depth', 'origin', 'direction', 'near', 'far', 'is_bkg', 'viewf_list')}
+    for cap, c in zip(caps, coords):
+        if c is None:
+            continue
+        c = c.cpu().numpy()
+        num = c.shape[0]
+        ref['color'].append((cap.image[c[:, 1], c[:, 0]] / 255).astype(np.float32))
+        ref['depth'].append(cap.depth_map[c[:, 1], c[:, 0]].astype(np.float32))
+        o, d = no.shot_rays(cap.intrinsic_matrix, cap.cam_pose.camera_to_world, c)
+        ref['origin'].append(np.asarray(o, dtype=np.float32))
+        ref['direction'].append(np.asarray(d, dtype=np.float32))
+        near, far = np.stack([[cap.near['bkg']]] * num), np.stack([[cap.far['bkg']]] * num)
+        ref['near'].append(near.astype(np.float32))
+        ref['far'].append(far.astype(np.float32))
+        ref['is_bkg'].append(np.ones_like(far).astype(np.int64))
+        ref['viewf_list'].append((np.ones_like(near) * cap.frame_id['frame_id'] / cap.frame_id['total_frames']).astype(np.float32))
+    for k, v in ref.items():
+        r = np.concatenate(v)
+        g = out[k].cpu().numpy()
+        assert g.shape == r.shape and g.dtype == r.dtype, (k, g.shape, r.shape, g.dtype, r.dtype)
+        if k in ('origin', 'direction'):
+            assert np.abs(g - r).max() < 2e-6, k
+        else:
+            assert np.array_equal(g, r), k
+    # the batch feeds the training step as is
+    full = b()
+    assert full['origin'].shape == (500, 3) and full['near'].shape == (500, 1) and full['is_bkg'].dtype == torch.long
+
+
+def test_human_ray_batcher():
+    """neuman_b200.data.HumanRayBatcher against a numpy restatement of HumanRayDataset.__getitem__
+    (datasets/human_rays.py:145-247, no patch) on the same pixels, with the near/far cache produced on the device
+    (data_io/cache_helper.py:16-36) checked against the oracle's geometry_guided_near_far."""
+    import types
+    from neuman_b200 import data as nd
+    from neuman_b200.render import SimpleCapture
+    from oracle import synth_smpl
+    rng = np.random.RandomState(5)
+    body = synth_smpl.random_body(seed=1, center=(0.0, 0.0, 2.5))
+    H, W = 40, 56
+    K = np.array([[70.0, 0, W / 2], [0, 70.0, H / 2], [0, 0, 1]])
+    cap = SimpleCapture(K, np.eye(4), H, W, near=0.2, far=6.0)
+    cap.near['human'], cap.far['human'] = 0.5, 5.0
+    cap.image = rng.randint(0, 256, (H, W, 3)).astype(np.uint8)
+    cap.mask = np.zeros((H, W), np.uint8)
+    cap.mask[10:30, 18:40] = 1
+    cap.binary_mask = cap.mask.copy()
+    cap.border_mask = np.zeros((H, W), np.uint8)
+    cap.border_mask[8:32, 16:42] = 1
+    cap.border_mask[10:30, 18:40] = 0
+    cap.frame_id = {'frame_id': 3, 'total_frames': 11}
+    nf = nd.near_far_cache_device(cap, body["verts"])
+    # cache vs the oracle on all pixels
+    xs, ys = np.meshgrid(np.arange(W), np.arange(H))
+    allc = np.stack([xs.ravel(), ys.ravel()], 1)
+    o, d = no.shot_rays(K, np.eye(4), allc)
+    near_r, far_r = no.geometry_guided_near_far(torch.from_numpy(np.asarray(o, np.float32)), torch.from_numpy(np.asarray(d, np.float32)),
+                                                torch.from_numpy(body["verts"].astype(np.float32)))
+    near_r, far_r = near_r.numpy().reshape(H, W), far_r.numpy().reshape(H, W)
+    got = nf.cpu().numpy()
+    hitm = near_r < far_r
+    assert hitm.sum() > 50 and np.array_equal(got[..., 0] < got[..., 1], hitm)
+    assert np.abs(got[..., 0][hitm] - near_r[hitm]).max() < 2e-5 and np.abs(got[..., 1][hitm] - far_r[hitm]).max() < 2e-5
+    opt = types.SimpleNamespace(rays_per_batch=300, penalize_lpips=0, dilation=5, body_rays_ratio=0.6, border_rays_ratio=0.1,
+                                bkg_rays_ratio=0.3)
+    b = nd.HumanRayBatcher(opt, [cap], [nf])
+    assert b.get_num_rays_dict(300) == {'num_body_rays': 180, 'num_border_rays': 30, 'num_bkg_rays': 90}
+    coords = b.sample_coords(0)
+    c = {k: v.cpu().numpy() for k, v in coords.items()}
+    assert (cap.mask[c['num_body_rays'][:, 1], c['num_body_rays'][:, 0]] != 0).all()
+    assert (cap.border_mask[c['num_border_rays'][:, 1], c['num_border_rays'][:, 0]] == 1).all()
+    assert (cap.mask[c['num_bkg_rays'][:, 1], c['num_bkg_rays'][:, 0]] == 0).all()
+    out = b.batch_from_coords(0, coords)
+    cache = got.astype(np.float64)
+    ref = {k: [] for k in ('color', 'human_near', 'human_far', 'bkg_near', 'bkg_far', 'is_bkg', 'is_hit')}
+    for key in b.KEYS:
+        cc = c[key]
+        num = cc.shape[0]
+        ref['color'].append((cap.image[cc[:, 1], cc[:, 0]] / 255).astype(np.float32))
+        ref['is_bkg'].append(1 - cap.binary_mask[cc[:, 1], cc[:, 0]])
+        ch = cache[cc[:, 1], cc[:, 0]]
+        valid = ch[..., 0] < ch[..., 1]
+        hn, hf = np.stack([[cap.near['human']]] * num), np.stack([[cap.far['human']]] * num)
+        hn[valid, 0] = ch[valid][:, 0]
+        hf[valid, 0] = ch[valid][:, 1]
+        ref['human_near'].append(hn.astype(np.float32))
+        ref['human_far'].append(hf.astype(np.float32))
+        ref['bkg_near'].append(np.stack([[cap.near['bkg']]] * num).astype(np.float32))
+        ref['bkg_far'].append(np.stack([[cap.far['bkg']]] * num).astype(np.float32))
+        ref['is_hit'].append(valid.astype(np.uint8))
+    for k, v in ref.items():
+        r, g = np.concatenate(v), out[k].cpu().numpy()
+        assert g.shape == r.shape, (k, g.shape, r.shape)
+        assert np.array_equal(g, r.astype(g.dtype)), k
+    assert out['is_bkg'].dtype == torch.long and out['is_hit'].dtype == torch.long and out['origin'].shape == (300, 3)
+    assert out['cur_view'] == 3 and abs(out['cur_view_f'] - 3 / 11) < 1e-12 and out['cap_id'] == 0
