@@ -350,18 +350,17 @@ def test_human_ray_batcher():
     cap.border_mask[8:32, 16:42] = 1
     cap.border_mask[10:30, 18:40] = 0
     cap.frame_id = {'frame_id': 3, 'total_frames': 11}
-    nf = nd.near_far_cache_device(cap, body["verts"])
-    # cache vs the oracle on all pixels
-    xs, ys = np.meshgrid(np.arange(W), np.arange(H))
-    allc = np.stack([xs.ravel(), ys.ravel()], 1)
-    o, d = no.shot_rays(K, np.eye(4), allc)
-    near_r, far_r = no.geometry_guided_near_far(torch.from_numpy(np.asarray(o, np.float32)), torch.from_numpy(np.asarray(d, np.float32)),
-                                                torch.from_numpy(body["verts"].astype(np.float32)))
+    nf = nd.near_far_cache_device(cap, body["verts"], body["geo_threshold"])
+    # cache vs the oracle on all pixels (grazing rays may flip: ill-conditioned sqrt, as in test_gpu_stages)
+    o, d = no.shot_rays(K, np.eye(4), no.all_pixel_coords(H, W))
+    near_r, far_r = no.geometry_guided_near_far(torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(body["verts"]),
+                                                body["geo_threshold"])
     near_r, far_r = near_r.numpy().reshape(H, W), far_r.numpy().reshape(H, W)
     got = nf.cpu().numpy()
-    hitm = near_r < far_r
-    assert hitm.sum() > 50 and np.array_equal(got[..., 0] < got[..., 1], hitm)
-    assert np.abs(got[..., 0][hitm] - near_r[hitm]).max() < 2e-5 and np.abs(got[..., 1][hitm] - far_r[hitm]).max() < 2e-5
+    solid = (near_r < far_r) & ((far_r - near_r) > 1e-3)
+    assert solid.sum() > 50 and np.isinf(near_r).sum() > 50
+    assert ((got[..., 0] < got[..., 1]) == (near_r < far_r))[solid | np.isinf(near_r)].all()
+    assert np.abs(got[..., 0][solid] - near_r[solid]).max() < 3e-5 and np.abs(got[..., 1][solid] - far_r[solid]).max() < 3e-5
     opt = types.SimpleNamespace(rays_per_batch=300, penalize_lpips=0, dilation=5, body_rays_ratio=0.6, border_rays_ratio=0.1,
                                 bkg_rays_ratio=0.3)
     b = nd.HumanRayBatcher(opt, [cap], [nf])
