@@ -95,3 +95,26 @@ def test_install_rebinds_reference_modules():
     out = mods["render_utils"].raw2outputs(raw, z, d)
     exp = no.raw2outputs(raw, z, d)
     assert torch.allclose(out[0], exp[0])
+
+
+@pytest.mark.reference
+def test_install_train_switch_keeps_cpu_paths_on_the_reference():
+    """install(train=True) wraps the trainers' entry points (Joiner.forward, raw2outputs, the samplers,
+    warp_samples_to_canonical_diff); with CPU tensors / grads every wrapper must fall through to the reference code."""
+    from oracle import ref_import, ref_opts
+    ref = ref_import.load()
+    mods = nb.install(train=True)
+    ru, ry, mv = mods["render_utils"], mods["ray_utils"], mods["vanilla"]
+    assert ry.warp_samples_to_canonical_diff.__name__ == "warp_samples_to_canonical_diff"
+    torch.manual_seed(0)
+    raw = torch.randn(3, 5, 4, requires_grad=True)
+    z, d = torch.sort(torch.rand(3, 5))[0], torch.randn(3, 3)
+    rgb = ru.raw2outputs(raw, z, d)[0]
+    rgb.sum().backward()                                  # reference torch ops: autograd works on the CPU
+    assert raw.grad is not None and torch.isfinite(raw.grad).all()
+    coarse, _ = mv.build_nerf(ref_opts.default_opt(use_cuda=False))
+    out = coarse(torch.randn(7, 3), torch.randn(7, 3))
+    assert out.shape == (7, 4) and out.requires_grad
+    batch = {'origin': torch.zeros(4, 3), 'direction': torch.randn(4, 3), 'near': torch.ones(4, 1) * 0.5, 'far': torch.ones(4, 1) * 2}
+    pts, dirs, zv = ry.ray_to_samples(batch, 6)
+    assert pts.shape == (4, 6, 3) and zv.shape == (4, 6)
