@@ -66,11 +66,12 @@ def _use_torch_chain():
 
 class _JoinerMLP(torch.autograd.Function):
     """forward: k_mlp_tc<.., kTrain> (csrc/mlp_tc.cu) = the inference kernel + an fp16 stash of every layer
-    output, the encodings and the ReLU sign words.
+    output and the ReLU sign words.
     backward: k_mlp_tc_bwd (csrc/mlp_tc_bwd.cu) runs the adjoint chain of NeRF.forward (models/vanilla.py:120-152)
     on the tensor cores and writes S * dL/d(pre-activation) of every layer in fp16 (S = power-of-two loss scale
-    chosen from max|dL/d raw| on the device); the weight gradients are the K = n GEMMs  g_l^T @ input_l  over the
-    stash (cuBLAS through torch.mm, fp16 operands / fp32 accumulate) and the bias gradients column sums.
+    chosen from max|dL/d raw| on the device); the weight and bias gradients are the K = n GEMMs  g_l^T @ input_l
+    over the stash: k_dw_gemm (csrc/dw_gemm.cu) for the nine 256-wide ones, cuBLAS (torch.mm, fp16 operands / fp32
+    accumulate) for the narrow ones against the encodings (k_encode_f16) and dL/d raw.
     Gradients go to the network parameters and, when they require grad, to the sample positions / directions
     (dL/d encoding by two small cuBLAS GEMMs on the gradient planes, then k_pe_backward), which is what the human
     trainer's differentiable warp and offset nets consume (trainers/human_nerf_trainer.py:241-278).

@@ -360,7 +360,8 @@ def test_human_ray_batcher():
     solid = (near_r < far_r) & ((far_r - near_r) > 1e-3)
     assert solid.sum() > 50 and np.isinf(near_r).sum() > 50
     assert ((got[..., 0] < got[..., 1]) == (near_r < far_r))[solid | np.isinf(near_r)].all()
-    assert np.abs(got[..., 0][solid] - near_r[solid]).max() < 3e-5 and np.abs(got[..., 1][solid] - far_r[solid]).max() < 3e-5
+    # fp32 on the device against the oracle's float64 rays at distance ~2.5: a few 1e-5
+    assert np.abs(got[..., 0][solid] - near_r[solid]).max() < 1e-4 and np.abs(got[..., 1][solid] - far_r[solid]).max() < 1e-4
     opt = types.SimpleNamespace(rays_per_batch=300, penalize_lpips=0, dilation=5, body_rays_ratio=0.6, border_rays_ratio=0.1,
                                 bkg_rays_ratio=0.3)
     b = nd.HumanRayBatcher(opt, [cap], [nf])
