@@ -118,3 +118,24 @@ def test_install_train_switch_keeps_cpu_paths_on_the_reference():
     batch = {'origin': torch.zeros(4, 3), 'direction': torch.randn(4, 3), 'near': torch.ones(4, 1) * 0.5, 'far': torch.ones(4, 1) * 2}
     pts, dirs, zv = ry.ray_to_samples(batch, 6)
     assert pts.shape == (4, 6, 3) and zv.shape == (4, 6)
+
+
+def test_frame_metrics_match_the_oracle(tmp_path):
+    """neuman_b200.metrics (render_test_views.py:27-41,88) against the scipy restatement of the scikit-image formulas."""
+    from neuman_b200 import metrics
+    from oracle import metrics_oracle as mo
+    rng = np.random.RandomState(0)
+    gt = rng.randint(0, 256, (37, 53, 3)).astype(np.uint8)
+    noise = rng.normal(0, 12, gt.shape)
+    pred = np.clip(gt.astype(np.float64) + noise, 0, 255).astype(np.uint8)
+    assert abs(metrics.psnr(gt, pred) - mo.peak_signal_noise_ratio(gt, pred)) < 1e-9
+    assert abs(metrics.ssim(pred, gt) - mo.structural_similarity(pred, gt)) < 1e-9
+    assert abs(metrics.ssim(gt, gt) - 1.0) < 1e-12
+    f = rng.uniform(-0.1, 1.1, (5, 7, 3)).astype(np.float32)
+    u = metrics.to_uint8(f).numpy()
+    assert u.dtype == np.uint8 and np.array_equal(u, np.floor(np.clip(f.astype(np.float64), 0, 1) * 255 + 0.5).astype(np.uint8))
+    metrics.save_png(str(tmp_path / "a.png"), f)
+    from PIL import Image
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "a.png")), u)
+    r = metrics.eval_metrics([gt, gt], [pred, gt])
+    assert set(r) == {"ssim", "psnr"} and np.isinf(r["psnr"])
