@@ -395,3 +395,48 @@ def test_human_ray_batcher():
         assert np.array_equal(g, r.astype(g.dtype)), k
     assert out['is_bkg'].dtype == torch.long and out['is_hit'].dtype == torch.long and out['origin'].shape == (300, 3)
     assert out['cur_view'] == 3 and abs(out['cur_view_f'] - 3 / 11) < 1e-12 and out['cap_id'] == 0
+
+
+def test_training_empty_and_scale_and_additivity():
+    """Size-independent properties of the training path at a size the oracle cannot reach:
+    empty batch; loss-scale invariance (gradients of c*L are c times the gradients of L for c over eight decades:
+    the power-of-two loss scale adapts on the device); additivity over the batch (gradients of a 300k-sample
+    batch = sum of the gradients of its two halves: persistent-kernel rounds, TMA tails and the split-K
+    reduction of k_dw_gemm agree)."""
+    from tests.util import product_nets
+    coarse, _, _ = product_nets(DEV)
+    j = coarse
+
+    def grads(pts, views, g):
+        j.zero_grad()
+        (j(pts, views) * g).sum().backward()
+        return {k: p.grad.detach().clone() for k, p in j.nerf.named_parameters()}
+    # empty
+    e = torch.zeros(0, 3, device=DEV)
+    raw = j(e, e)
+    assert raw.shape == (0, 4)
+    raw.sum().backward()
+    assert all(p.grad is not None and float(p.grad.abs().max()) == 0.0 for p in j.nerf.parameters())
+    # loss-scale invariance
+    torch.manual_seed(3)
+    n = 5000
+    pts = torch.randn(n, 3, device=DEV)
+    views = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV), dim=-1)
+    g = torch.randn(n, 4, device=DEV)
+    base = grads(pts, views, g)
+    for c in (1e-4, 1e4):
+        sc = grads(pts, views, g * c)
+        for k in base:
+            assert torch.isfinite(sc[k]).all()
+            assert _rel(sc[k] / c, base[k]) < 1e-3, (c, k, _rel(sc[k] / c, base[k]))
+    # additivity at scale (several persistent rounds per kernel)
+    n = 300000 + 77
+    pts = torch.randn(n, 3, device=DEV)
+    views = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV), dim=-1)
+    g = torch.randn(n, 4, device=DEV) * (torch.rand(n, 1, device=DEV) < 0.5)      # half of the rows carry no gradient
+    h = n // 2 + 13
+    full = grads(pts, views, g)
+    a = grads(pts[:h], views[:h], g[:h])
+    b = grads(pts[h:], views[h:], g[h:])
+    for k in full:
+        assert _rel(a[k] + b[k], full[k]) < 2e-3, (k, _rel(a[k] + b[k], full[k]))
