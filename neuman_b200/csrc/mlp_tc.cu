@@ -212,12 +212,17 @@ __device__ __forceinline__ uint32_t epi_sub16(const uint32_t (&v)[16], const flo
     *reinterpret_cast<uint4*>(grow + c0 + 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
   }
   // ReLU sign word of these 16 outputs (training kernel only): bit j = [column c0+2j > 0], bit 8+j = [column
-  // c0+2j+1 > 0].  The outputs are non-negative f16, so adding 0x7fff to a half carries into its bit 15 exactly
-  // when it is non-zero; three integer ops per register.
+  // c0+2j+1 > 0].  The INT32 pipe runs at half the FP rate and this epilogue is short of issue slots in the training
+  // kernel, so the compare is a packed-half HSET2 (one per register, FP16 pipe) that yields 0xFFFF per positive half,
+  // and only one LOP3 per register (pick bit j of each half, OR into the word) plus one PRMT remain on the INT pipe.
   uint32_t acc = 0;
+  const __half2 zero2 = __float2half2_rn(0.f);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc = (acc >> 1) | ((packed[j] + 0x7fff7fffu) & 0x80008000u);
-  return ((acc >> 8) & 0xffu) | ((acc >> 16) & 0xff00u);
+  for (int j = 0; j < 8; ++j) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&packed[j]);
+    acc |= __hgt2_mask(h, zero2) & ((1u << j) | (1u << (16 + j)));
+  }
+  return __byte_perm(acc, 0u, 0x4420);          // byte 0 = low halves, byte 1 = high halves
 }
 
 // Drains `ncols` accumulator columns of this thread's TMEM lane into the activation block, software
