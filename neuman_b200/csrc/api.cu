@@ -30,6 +30,7 @@ static void free_net(NmNet& n) {
   if (n.f16) cudaFree(n.f16);
   if (n.tc_bias) cudaFree(n.tc_bias);
   if (n.f16_bwd) cudaFree(n.f16_bwd);
+  if (n.bw_wrgb) cudaFree(n.bw_wrgb);
   n = NmNet();
 }
 

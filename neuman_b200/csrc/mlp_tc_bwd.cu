@@ -7,7 +7,7 @@
 //   b0: dF   = dVpre @ Wviews[:, :256]                        (K = 128)
 //   b1: dX8  = dF @ Wfeature + g_alpha * w_alpha ;  dpre7 = dX8 * [X8 > 0]
 //   b2..b8 (l = 7..1): dX_{l-1} = dpre_l @ W_l[:, -256:] ;   dpre_{l-1} = dX_{l-1} * [X_{l-1} > 0]
-// Every dpre_l, dF and dVpre is written to HBM in fp16 (they are the left operands of the weight-gradient
+// Every dpre_l, dF and dVpre is written to HBM in fp16 by TMA stores from the A buffer (they are the left operands of the weight-gradient
 // GEMMs dW_l = dpre_l^T @ X_{l-1}, done by the caller with the forward's activation stash), and stays in shared
 // memory as the next step's A operand.  The ReLU masks come from the forward's 256-bit sign words.
 // Gradients w.r.t. the sample positions are not produced (the trainers treat samples as constants).
@@ -18,6 +18,12 @@
 #define BW_STEPS 9
 __host__ __device__ constexpr int bw_nkb(int b) { return b == 0 ? 2 : 4; }
 #define BW_SLABS (2 + 8 * 4)
+
+// rgb_linear.weight as [3][128] for the head (dV = g_rgb @ Wrgb): every thread needs all 384 values, with indices
+// that are compile-time constants after unrolling, so they are folded into the FFMAs as constant-bank operands
+// (read from shared memory this cost 384 LDS per thread and made the head the slowest step of a round: 17k cycles).
+// Copied from the net's packed image before each launch (stream-ordered, device to device).
+__constant__ float c_bw_wrgb[384];
 
 template <int kPair>
 struct BwCfg {
@@ -30,8 +36,8 @@ struct BwCfg {
   static constexpr int OFF_BAR = OFF_RING + NSLOT * SLOT_BYTES;
   static constexpr int N_BAR = 3 * NSLOT + 2 * NT;          // full peer_full empty | tmem_full act_ready
   static constexpr int OFF_TMEMPTR = OFF_BAR + 8 * N_BAR;
-  static constexpr int OFF_CONST = (OFF_TMEMPTR + 16 + 127) & ~127;   // w_alpha[256] + Wrgb[3][128] fp32
-  static constexpr int SMEM_USED = OFF_CONST + 1024 + 1536;
+  static constexpr int OFF_CONST = (OFF_TMEMPTR + 16 + 127) & ~127;   // w_alpha[256] fp32
+  static constexpr int SMEM_USED = OFF_CONST + 1024;
   static constexpr int SMEM_BYTES = SMEM_USED + 1024;
 };
 
@@ -40,7 +46,6 @@ struct BwParams {
   uint32_t image_bytes;
   const float* d_raw;       // [n][4] fp32 dL/d(r,g,b,sigma)
   const float* scale;       // device scalar: loss scale S (a power of two)
-  const float* w_rgb_t;     // [128][3] fp32 rgb_linear.weight transposed (api.cu layout)
   const float* w_alpha;     // [256] fp32 alpha_linear.weight
   const __half* st_v;       // [n][128] forward stash: views layer post-ReLU
   const uint32_t* st_m;     // [8][n][8] forward stash: ReLU sign words of pts_linears 0..7
@@ -48,14 +53,15 @@ struct BwParams {
   __half* g_f;              // [n][256]    out: S * dL/d feature
   __half* g_v;              // [n][128]    out: S * dL/d(pre-activation of views_linears.0)
   long long n, n_tiles;
-  CUtensorMap map_pre, map_f;   // TMA store maps of g_pre / g_f
+  CUtensorMap map_pre, map_f, map_v;   // TMA store maps of g_pre / g_f / g_v
+  long long* trace;             // optional debug timeline (tools/tc_trace.py bwd): same layout as mlp_tc.cu's
 };
 
 // 16 accumulator columns [c0, c0+16) of one row: (+ rank-1 alpha term), ReLU mask from sign bits, pack,
-// swizzled store into the next A operand, 32-byte store into the HBM gradient stash
-template <bool ALPHA, bool MASK, bool TO_ACT>
+// swizzled store into the next A operand (from where a TMA store takes it to the HBM gradient plane)
+template <bool ALPHA, bool MASK>
 __device__ __forceinline__ void bw_sub16(const uint32_t (&v)[16], int c0, float da, const float* s_walpha, uint32_t mbits,
-                                         uint8_t* act, int row, __half* grow) {
+                                         uint8_t* act, int row) {
   float x[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) {
@@ -72,22 +78,16 @@ __device__ __forceinline__ void bw_sub16(const uint32_t (&v)[16], int c0, float 
   uint32_t packed[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) packed[j] = pack_f16x2(x[2 * j], x[2 * j + 1], false);
-  if (TO_ACT) {
-    uint8_t* blk = act + (c0 >> 6) * TC_KB_BYTES + row * 128;
-    const int ch0 = (c0 & 63) >> 3;
-    *reinterpret_cast<uint4*>(blk + ((ch0 ^ (row & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    *reinterpret_cast<uint4*>(blk + (((ch0 + 1) ^ (row & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-  }
-  if (grow) {
-    *reinterpret_cast<uint4*>(grow + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    *reinterpret_cast<uint4*>(grow + c0 + 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-  }
+  uint8_t* blk = act + (c0 >> 6) * TC_KB_BYTES + row * 128;
+  const int ch0 = (c0 & 63) >> 3;
+  *reinterpret_cast<uint4*>(blk + ((ch0 ^ (row & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  *reinterpret_cast<uint4*>(blk + (((ch0 + 1) ^ (row & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
 }
 
 // drains 128 accumulator columns [cbase, cbase+128) of this thread's TMEM lane; mask = 128 sign bits
-template <bool ALPHA, bool MASK, bool TO_ACT>
+template <bool ALPHA, bool MASK>
 __device__ __forceinline__ void bw_step(uint32_t t_lane, int cbase, float da, const float* s_walpha, const uint4& mask,
-                                        uint8_t* act, int row, __half* grow) {
+                                        uint8_t* act, int row) {
   uint32_t v0[16], v1[16];
   const uint32_t mw[4] = {mask.x, mask.y, mask.z, mask.w};
   tmem_ld16(t_lane + cbase, v0);
@@ -96,12 +96,19 @@ __device__ __forceinline__ void bw_step(uint32_t t_lane, int cbase, float da, co
     const int c = cbase + 32 * q;
     tmem_wait_ld();
     tmem_ld16(t_lane + c + 16, v1);
-    bw_sub16<ALPHA, MASK, TO_ACT>(v0, c, da, s_walpha, mw[q] & 0xffffu, act, row, grow);
+    bw_sub16<ALPHA, MASK>(v0, c, da, s_walpha, mw[q] & 0xffffu, act, row);
     tmem_wait_ld();
     if (q < 3) tmem_ld16(t_lane + c + 32, v0);
-    bw_sub16<ALPHA, MASK, TO_ACT>(v1, c + 16, da, s_walpha, mw[q] >> 16, act, row, grow);
+    bw_sub16<ALPHA, MASK>(v1, c + 16, da, s_walpha, mw[q] >> 16, act, row);
   }
 }
+
+// debug timeline, as in mlp_tc.cu: role 0 = MMA issuer (0: operand ready seen, 1: step issued + committed), role 1 =
+// epilogue warp 2 lane 0 (0: accumulator ready seen, 1: drained, 2: handed over); tile 0 of CTAs 0 / 1 only
+#define BW_TRACE(role, ev, idx)                                                                             \
+  do {                                                                                                      \
+    if (P.trace && blockIdx.x < 2 && (idx) < 256) P.trace[((blockIdx.x * 2 + (role)) * 4 + (ev)) * 256 + (idx)] = clock64(); \
+  } while (0)
 
 template <int kPair>
 __global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const __grid_constant__ BwParams P) {
@@ -125,7 +132,6 @@ __global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const _
   auto bar_aready = [&](int t) { return sbase + C::OFF_BAR + 8 * (3 * NSLOT + NT + t); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEMPTR);
   float* s_walpha = reinterpret_cast<float*>(smem + C::OFF_CONST);
-  float* s_wrgb = s_walpha + 256;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_peer(i), 1); mbar_init(bar_empty(i), 1); }
@@ -135,7 +141,6 @@ __global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const _
   if (threadIdx.x >= 64) {
     const int e = threadIdx.x - 64;
     s_walpha[e] = __ldg(P.w_alpha + e);
-    for (int k = e; k < 384; k += 256) s_wrgb[k] = __ldg(P.w_rgb_t + (k & 127) * 3 + (k >> 7));   // -> [3][128]
   }
   if (warp == 1) {
     tmem_alloc<kPair>(smem_u32(tmem_ptr_smem), 512);
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const _
           for (int t = 0; t < NT; ++t) {
             mbar_wait(bar_aready(t), nstep & 1);
             tc_fence_after();
+            if (t == 0 && issuer) BW_TRACE(0, 0, nstep);
             const uint32_t d_tmem = tmem_base + t * 256;
             for (int kb = 0; kb < nkb; ++kb) {
               const uint32_t q = q0 + kb, slot = q % NSLOT, gen = q / NSLOT;
@@ -196,7 +202,10 @@ __global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const _
               }
               __syncwarp();
             }
-            if (issuer) umma_commit<kPair>(bar_tfull(t));
+            if (issuer) {
+              umma_commit<kPair>(bar_tfull(t));
+              if (t == 0) BW_TRACE(0, 1, nstep);
+            }
             __syncwarp();
           }
           q0 += nkb;
@@ -249,17 +258,12 @@ __global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const _
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int c = 8 * j + 2 * k;
-          float x0 = fmaf(gr.x, s_wrgb[c], fmaf(gr.y, s_wrgb[128 + c], gr.z * s_wrgb[256 + c]));
-          float x1 = fmaf(gr.x, s_wrgb[c + 1], fmaf(gr.y, s_wrgb[129 + c], gr.z * s_wrgb[257 + c]));
+          float x0 = fmaf(gr.x, c_bw_wrgb[c], fmaf(gr.y, c_bw_wrgb[128 + c], gr.z * c_bw_wrgb[256 + c]));
+          float x1 = fmaf(gr.x, c_bw_wrgb[c + 1], fmaf(gr.y, c_bw_wrgb[129 + c], gr.z * c_bw_wrgb[257 + c]));
           if (!(vw[k] & 0x7fffu)) x0 = 0.f;                     // V is post-ReLU: zero <=> inactive
           if (!(vw[k] & 0x7fff0000u)) x1 = 0.f;
           head[4 * j + k] = pack_f16x2(x0, x1, false);
         }
-      }
-      if (ok) {
-        uint4* dst = reinterpret_cast<uint4*>(P.g_v + (size_t)i * 128);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) dst[j] = make_uint4(head[4 * j], head[4 * j + 1], head[4 * j + 2], head[4 * j + 3]);
       }
     };
     auto store_head = [&](int t) {                  // 128 channels -> A k-blocks 0 and 1 of tile t
@@ -273,16 +277,33 @@ __global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const _
     };
     auto load_mask = [&](long long round, int t, int plane) {
       if (!tile_valid(round, t)) return make_uint4(0, 0, 0, 0);
-      return __ldg(reinterpret_cast<const uint4*>(P.st_m + ((size_t)plane * P.n + sample_index(round, t)) * 8) + g);
+      return __ldg(reinterpret_cast<const uint4*>(P.st_m + ((size_t)plane * P.n + sample_index(round, t)) * 8) + (g ^ t));
     };
     if (n_rounds > 0) build_head(0);
 
+    // Column ownership: for tile t this thread drains columns [(g ^ t) * 128, +128) = A k-blocks 2(g^t), 2(g^t)+1 of its
+    // row in every step.  The warpgroup that builds the head of tile t (g == t) is therefore the one that owns k-blocks
+    // 0 and 1 of that tile, and every write / TMA read of a slice of the A buffer is ordered inside one warp.
     for (long long round = 0; round < n_rounds; ++round) {
       float da[NT];
       uint4 mnext[NT];
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        if (g == t) store_head(t);
+        if (g == t) {
+          // the last step of the previous round stored this slice by TMA: it must have been read
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          store_head(t);
+          fence_async_smem();
+          __syncwarp();
+          const long long i0 = sample_index(round, t) - lane;
+          if (lane == 0 && i0 < P.n) {                  // dL/d(views pre-activation) leaves from the A buffer as well
+            const uint32_t src = sbase + C::OFF_ACT + t * 4 * TC_KB_BYTES + quad * 32 * 128;
+            tma_store_3d(&P.map_v, src, 0, (int)i0, 0);
+            tma_store_3d(&P.map_v, src + TC_KB_BYTES, 64, (int)i0, 0);
+            tma_store_commit();
+          }
+        }
         publish(t);
         da[t] = tile_valid(round, t) ? S * __ldg(P.d_raw + 4 * sample_index(round, t) + 3) : 0.f;
         mnext[t] = load_mask(round, t, 7);          // step b1 masks with [X8 > 0] = plane 7
@@ -299,51 +320,36 @@ __global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const _
         for (int t = 0; t < NT; ++t) {
           uint8_t* act = smem + C::OFF_ACT + t * 4 * TC_KB_BYTES;
           const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + t * 256;
+          const int gc = g ^ t;                       // column half of this thread for tile t
           mbar_wait(bar_tfull(t), nstep & 1);
           tc_fence_after();
-          // steps 0..7 leave through TMA from the A buffer (below); the last step, which must not touch the A
-          // buffer, stores its rows to HBM directly
-          __half* grow = nullptr;
-          if (b == BW_STEPS - 1 && tile_valid(round, t)) grow = P.g_pre + (size_t)sample_index(round, t) * 256;
-          // this warp's slice is the source of the store issued one step ago (the other tile's may still fly)
-          if (lane == 0) tma_store_wait_read<1>();
+          if (t == 0 && ew == 0 && lane == 0) BW_TRACE(1, 0, nstep);
+          // this warp's slice is the source of the TMA store it issued one step ago (the other tile's may still
+          // fly); in step 0 the head's store of this round may be the most recent one: wait for everything
+          if (lane == 0) { if (b == 0) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
           __syncwarp();
-          // the last step's result (dpre of layer 0) only goes to HBM: the tile's A buffer already belongs to the
-          // next round's head, which the other warpgroup may be writing
-          if (b == 0) bw_step<false, false, true>(t_lane, g * 128, 0.f, s_walpha, mcur[t], act, row, grow);
-          else if (b == 1) bw_step<true, true, true>(t_lane, g * 128, da[t], s_walpha, mcur[t], act, row, grow);
-          else if (b < BW_STEPS - 1) bw_step<false, true, true>(t_lane, g * 128, 0.f, s_walpha, mcur[t], act, row, grow);
-          else bw_step<false, true, false>(t_lane, g * 128, 0.f, s_walpha, mcur[t], act, row, grow);
+          if (b == 0) bw_step<false, false>(t_lane, gc * 128, 0.f, s_walpha, mcur[t], act, row);
+          else if (b == 1) bw_step<true, true>(t_lane, gc * 128, da[t], s_walpha, mcur[t], act, row);
+          else bw_step<false, true>(t_lane, gc * 128, 0.f, s_walpha, mcur[t], act, row);
+          if (t == 0 && ew == 0 && lane == 0) BW_TRACE(1, 1, nstep);
+          const long long i0 = sample_index(round, t) - lane;              // first row of this warp
+          const bool issue = lane == 0 && i0 < P.n;
+          const uint32_t src = sbase + C::OFF_ACT + (t * 4 + 2 * gc) * TC_KB_BYTES + quad * 32 * 128;
+          const CUtensorMap* m = b == 0 ? &P.map_f : &P.map_pre;
+          const int plane = b == 0 ? 0 : 8 - b;
           if (b < BW_STEPS - 1) {
-            const long long i0 = sample_index(round, t) - lane;              // first row of this warp
-            const bool issue = lane == 0 && i0 < P.n;
-            const uint32_t src = sbase + C::OFF_ACT + (t * 4 + 2 * g) * TC_KB_BYTES + quad * 32 * 128;
-            const CUtensorMap* m = b == 0 ? &P.map_f : &P.map_pre;
-            const int plane = b == 0 ? 0 : 8 - b;
-            if (b < BW_STEPS - 2) {
-              // the MMA thread is told first: the store and the next step's MMAs only read this slice
-              publish(t);
-              if (issue) {
-                tma_store_3d(m, src, 128 * g, (int)i0, plane);
-                tma_store_3d(m, src + TC_KB_BYTES, 128 * g + 64, (int)i0, plane);
-                tma_store_commit();
-              }
-            } else {
-              // after step 7 the tile's A buffer passes to the next round's head, written by the other
-              // warpgroup: the store must have finished reading before anyone is told to go on
-              fence_async_smem();
-              __syncwarp();
-              if (issue) {
-                tma_store_3d(m, src, 128 * g, (int)i0, plane);
-                tma_store_3d(m, src + TC_KB_BYTES, 128 * g + 64, (int)i0, plane);
-                tma_store_commit();
-                tma_store_wait_read<0>();
-              }
-              publish(t);
-            }
+            publish(t);                               // the MMA thread first: the store and the next MMAs only read
           } else {
+            fence_async_smem();                       // last step: nothing to hand over, only the store
             tc_fence_before();
+            __syncwarp();
           }
+          if (issue) {
+            tma_store_3d(m, src, 128 * gc, (int)i0, plane);
+            tma_store_3d(m, src + TC_KB_BYTES, 128 * gc + 64, (int)i0, plane);
+            tma_store_commit();
+          }
+          if (t == 0 && ew == 0 && lane == 0) BW_TRACE(1, 2, nstep);
         }
         if (b == 4 && round + 1 < n_rounds) build_head(round + 1);
       }
@@ -377,9 +383,11 @@ __device__ __forceinline__ float bw_src_weight(const BwPackSrc& S, int b, int n,
   return S.wt[l][(size_t)((l == 5 ? NM_POS_PE : 0) + n) * 256 + out];           // layer 5 input = [PE(63), hidden]
 }
 
-__global__ void k_bw_pack(BwPackSrc S, int kpair, uint32_t image_bytes, __half* __restrict__ out) {
+__global__ void k_bw_pack(BwPackSrc S, int kpair, uint32_t image_bytes, __half* __restrict__ out, const float* __restrict__ rgb_t,
+                          float* __restrict__ wrgb) {
   const int rank = blockIdx.y;
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (rank == 0 && e < 384) wrgb[e] = rgb_t[(e & 127) * 3 + (e >> 7)];      // [128][3] (api.cu layout) -> [3][128]
   if (e * 2 >= image_bytes) return;
   const uint32_t slot_bytes = 32768u / kpair;
   const uint32_t byte = (uint32_t)(e * 2);
@@ -487,11 +495,12 @@ int nm_tc_pack_bwd(nm_ctx* ctx, NmNet& net, cudaStream_t st) {
   const uint32_t image_bytes = (uint32_t)BW_SLABS * (32768u / kpair);
   const size_t halfs = (size_t)kpair * image_bytes / 2;
   if (!net.f16_bwd) NM_CHECK_CUDA(ctx, cudaMalloc(&net.f16_bwd, halfs * sizeof(__half)));
+  if (!net.bw_wrgb) NM_CHECK_CUDA(ctx, cudaMalloc(&net.bw_wrgb, 384 * sizeof(float)));
   BwPackSrc S;
   for (int l = 0; l < 8; ++l) S.wt[l] = net.f32 + net.o_pts_w[l];
   S.feat_t = net.f32 + net.o_feat_w; S.views_t = net.f32 + net.o_views_w;
   dim3 grid((unsigned)((image_bytes / 2 + 255) / 256), kpair);
-  k_bw_pack<<<grid, 256, 0, st>>>(S, kpair, image_bytes, net.f16_bwd);
+  k_bw_pack<<<grid, 256, 0, st>>>(S, kpair, image_bytes, net.f16_bwd, net.f32 + net.o_rgb_w, net.bw_wrgb);
   NM_CHECK_LAUNCH(ctx);
   net.bwd_packed = true;
   return NM_OK;
@@ -535,13 +544,17 @@ int nm_tc_backward(nm_ctx* ctx, NmNet& net, const float* d_raw, const float* sca
   P.wimg = reinterpret_cast<const uint8_t*>(net.f16_bwd);
   P.image_bytes = (uint32_t)BW_SLABS * (32768u / kpair);
   P.d_raw = d_raw; P.scale = scale;
-  P.w_rgb_t = net.f32 + net.o_rgb_w; P.w_alpha = net.f32 + net.o_alpha_w;
+  P.w_alpha = net.f32 + net.o_alpha_w;
+  NM_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_bw_wrgb, net.bw_wrgb, 384 * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
   P.st_v = st_v; P.st_m = st_m;
   P.g_pre = g_pre; P.g_f = g_f; P.g_v = g_v;
   P.n = n;
   P.n_tiles = (n + 128 * kpair - 1) / (128 * kpair);
+  P.trace = nullptr;
+  if (const char* e = getenv("NEUMAN_TC_TRACE_BWD")) P.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
   if (n >= (int64_t)0x7fff0000) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_backward: n too large for one call");
-  if (tc_make_store_map(&P.map_pre, g_pre, 8, (uint64_t)n, 256) || tc_make_store_map(&P.map_f, g_f, 1, (uint64_t)n, 256))
+  if (tc_make_store_map(&P.map_pre, g_pre, 8, (uint64_t)n, 256) || tc_make_store_map(&P.map_f, g_f, 1, (uint64_t)n, 256) ||
+      tc_make_store_map(&P.map_v, g_v, 1, (uint64_t)n, 128))
     NM_FAIL(ctx, NM_ERR_CUDA, "nm_mlp_backward: cuTensorMapEncodeTiled failed");
   return kpair == 2 ? launch_bwd<2>(ctx, P, st) : launch_bwd<1>(ctx, P, st);
 }

@@ -32,6 +32,7 @@ struct NmNet {
   size_t f16_halfs = 0;
   float* tc_bias = nullptr;         // concatenated fp32 biases + alpha weights for the epilogues
   __half* f16_bwd = nullptr;        // transposed slabs for the backward chain (mlp_tc_bwd.cu), packed on first use
+  float* bw_wrgb = nullptr;         // rgb_linear.weight as [3][128] for the backward kernel's constant bank
   bool bwd_packed = false;
   nm_nerf_desc pe_desc{};           // description the uploaded encoding tables were built from
   bool pe_valid = false;
