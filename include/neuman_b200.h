@@ -86,8 +86,9 @@ int nm_mlp_forward(nm_ctx* ctx, int slot, int mode, const float* pts, const floa
 /* Training forward of the same network (train.py -> trainers/*: Joiner.forward under autograd): as
  * nm_mlp_forward in NM_MLP_TC_F16 mode, and additionally writes the fp16 activations the backward
  * pass needs.  stash_x: [8][n][256] post-ReLU outputs of pts_linears 0..7; stash_f: [n][256]
- * feature_linear output; stash_v: [n][128] views_linears.0 post-ReLU; stash_m: [8][n][8] uint32 ReLU sign
- * words (16 bits per 16 outputs: bit j = [output 2j > 0], bit 8+j = [output 2j+1 > 0]). */
+ * feature_linear output; stash_v: [n][128] views_linears.0 post-ReLU; stash_m: [9][n][8] uint32 ReLU sign
+ * words (16 bits per 16 outputs: bit j = [output 2j > 0], bit 8+j = [output 2j+1 > 0]): planes 0..7 =
+ * pts_linears 0..7, plane 8 = views_linears.0 (words 0..3). */
 int nm_mlp_forward_train(nm_ctx* ctx, int slot, const float* pts, const float* views, int64_t n,
                          int32_t views_per_ray, float* raw, void* stash_x, void* stash_f, void* stash_v,
                          void* stash_m, void* stream);
@@ -102,7 +103,8 @@ int nm_encode_f16(nm_ctx* ctx, int slot, int32_t which, const float* x, int64_t 
 /* Adjoint of NeRF.forward (models/vanilla.py:120-152) with respect to the layer pre-activations
  * (what torch autograd computes inside loss.backward() for trainers/vanilla_nerf_trainer.py:222).
  * d_raw: [n,4] fp32 dL/d(raw); loss_scale: device pointer to one float S (a power of two; all outputs
- * are S * gradient in fp16).  Outputs: g_pre [8][n][256] = dL/d(pre-activation of pts_linears l),
+ * are S * gradient in fp16); stash_m: the forward's [9][n][8] sign words (stash_v is accepted for symmetry and
+ * not read).  Outputs: g_pre [8][n][256] = dL/d(pre-activation of pts_linears l),
  * g_f [n][256] = dL/d(feature), g_v [n][128] = dL/d(pre-activation of views_linears.0).  The weight
  * gradients are then dW_l = g_l^T @ input_l over the forward stash (GEMMs with K = n, left to the
  * caller's BLAS), the bias gradients the column sums of g_l. */

@@ -90,7 +90,7 @@ class _JoinerMLP(torch.autograd.Function):
         h = dict(device=dev, dtype=torch.float16)
         sx, sf = torch.empty(8, n, 256, **h), torch.empty(n, 256, **h)
         sv = torch.empty(n, 128, **h)
-        sm = torch.empty(8, n, 8, device=dev, dtype=torch.int32)
+        sm = torch.empty(9, n, 8, device=dev, dtype=torch.int32)     # planes 0..7: pts_linears, 8: views layer
         raw = torch.empty(n, 4, device=dev, dtype=torch.float32)
         if n:
             ctx.check(ctx.lib.nm_mlp_forward_train(ctx.h, slot, _p(pts), _p(views), n, 0, _p(raw), _p(sx), _p(sf), _p(sv),

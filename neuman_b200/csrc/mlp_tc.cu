@@ -77,7 +77,8 @@ struct TcParams {
   __half* st_x;             // [8][n][256] post-ReLU outputs of layers 0..7
   __half* st_f;             // [n][256]    feature_linear output
   __half* st_v;             // [n][128]    views layer post-ReLU
-  uint32_t* st_m;           // [8][n][8]   sign words, 16 bits per 16 columns: bit j = [col 2j > 0], bit 8+j = [col 2j+1 > 0]
+  uint32_t* st_m;           // [9][n][8]   sign words, 16 bits per 16 columns: bit j = [col 2j > 0], bit 8+j = [col 2j+1 > 0];
+                            //             planes 0..7 = pts_linears, plane 8 = views layer (words 0..3 used)
   CUtensorMap map_x, map_f, map_v;   // TMA store maps of st_x / st_f / st_v (kTrain only)
   int dbg;                  // debug (NEUMAN_TC_DEBUG): bit 0 = training kernel skips its TMA stash stores (timing experiments only)
   long long* trace;         // optional debug timeline (tools/tc_trace.py): [cta<2][role<2][event<4][256] clock64 stamps
@@ -486,6 +487,8 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
             else epi_step<true, false, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row, grow, signs);
             if (kTrain && s < 8 && tile_valid(round, t))
               reinterpret_cast<uint4*>(P.st_m + ((size_t)s * P.in.n + sample_index(round, t)) * 8)[g] = signs;
+            if (kTrain && s == 9 && tile_valid(round, t))   // views layer: 64 columns per thread -> words 2g, 2g+1 of plane 8
+              reinterpret_cast<uint2*>(P.st_m + ((size_t)8 * P.in.n + sample_index(round, t)) * 8)[g] = make_uint2(signs.x, signs.y);
             if (s == 7 && g == 1) s_alpha[t * 128 + row] = (alpha[t][0] + alpha[t][1]) + (alpha[t][2] + alpha[t][3]);
             if (s == 4 && g == t) { wait_pe_slot(round, 1, t); store_row_swizzled(pebuf, row, pe_pos, 8); }   // skip input (:131)
             if (s == 8 && g == t) { wait_pe_slot(round, 2, t); store_row_swizzled(pebuf, row, pe_dir, 4); }   // view dirs (:137)

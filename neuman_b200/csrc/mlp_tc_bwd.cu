@@ -3,7 +3,7 @@
 // TMEM accumulators, bulk-TMA weight ring, persistent CTA pairs, activations kept on chip).
 //
 // For every sample row, with g = dL/d raw (4 values) scaled by the loss scale S:
-//   dVpre = (g_rgb @ Wrgb) * [V > 0]                         (epilogue threads, K = 3)
+//   dVpre = (g_rgb @ Wrgb) * [V > 0]                         (epilogue threads, K = 3; [V > 0] from sign words)
 //   b0: dF   = dVpre @ Wviews[:, :256]                        (K = 128)
 //   b1: dX8  = dF @ Wfeature + g_alpha * w_alpha ;  dpre7 = dX8 * [X8 > 0]
 //   b2..b8 (l = 7..1): dX_{l-1} = dpre_l @ W_l[:, -256:] ;   dpre_{l-1} = dX_{l-1} * [X_{l-1} > 0]
@@ -47,8 +47,7 @@ struct BwParams {
   const float* d_raw;       // [n][4] fp32 dL/d(r,g,b,sigma)
   const float* scale;       // device scalar: loss scale S (a power of two)
   const float* w_alpha;     // [256] fp32 alpha_linear.weight
-  const __half* st_v;       // [n][128] forward stash: views layer post-ReLU
-  const uint32_t* st_m;     // [8][n][8] forward stash: ReLU sign words of pts_linears 0..7
+  const uint32_t* st_m;     // [9][n][8] forward stash: ReLU sign words of pts_linears 0..7 and (plane 8, 4 words) of the views layer
   __half* g_pre;            // [8][n][256] out: S * dL/d(pre-activation of pts_linears l)
   __half* g_f;              // [n][256]    out: S * dL/d feature
   __half* g_v;              // [n][128]    out: S * dL/d(pre-activation of views_linears.0)
@@ -244,24 +243,33 @@ __global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const _
     };
     // head of tile g, round r: dVpre row (128 channels) in registers, computed one round ahead
     uint32_t head[64];
-    auto build_head = [&](long long round) {
-      const bool ok = tile_valid(round, g);
-      const long long i = ok ? sample_index(round, g) : 0;
-      float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok) gr = __ldg(reinterpret_cast<const float4*>(P.d_raw) + i);
-      gr.x *= S; gr.y *= S; gr.z *= S;
-      const uint4* vrow = reinterpret_cast<const uint4*>(P.st_v + (size_t)i * 128);
+    // The head needs, per row, dL/d raw (16 B) and the 128 ReLU sign bits of the views layer (16 B): both are
+    // fetched a few steps before they are used (prefetch_head), so building the head is pure arithmetic.
+    float4 gr_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint4 vm_next = make_uint4(0, 0, 0, 0);
+    auto prefetch_head = [&](long long round) {
+      gr_next = make_float4(0.f, 0.f, 0.f, 0.f);
+      vm_next = make_uint4(0, 0, 0, 0);
+      if (tile_valid(round, g)) {
+        const long long i = sample_index(round, g);
+        gr_next = __ldg(reinterpret_cast<const float4*>(P.d_raw) + i);
+        vm_next = __ldg(reinterpret_cast<const uint4*>(P.st_m + ((size_t)8 * P.n + i) * 8));
+      }
+    };
+    auto build_head = [&]() {
+      const float gx = gr_next.x * S, gy = gr_next.y * S, gz = gr_next.z * S;
+      const uint32_t vw[4] = {vm_next.x, vm_next.y, vm_next.z, vm_next.w};
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        uint4 vv = ok ? __ldg(vrow + j) : make_uint4(0, 0, 0, 0);
-        const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
+        // columns 8j .. 8j+7 live in word j/4, 16-bit half (j/2)%2; pair p of that group: bit p = even column, bit 8+p = odd
+        const uint32_t bits16 = vw[j >> 2] >> (16 * ((j >> 1) & 1));
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int c = 8 * j + 2 * k;
-          float x0 = fmaf(gr.x, c_bw_wrgb[c], fmaf(gr.y, c_bw_wrgb[128 + c], gr.z * c_bw_wrgb[256 + c]));
-          float x1 = fmaf(gr.x, c_bw_wrgb[c + 1], fmaf(gr.y, c_bw_wrgb[129 + c], gr.z * c_bw_wrgb[257 + c]));
-          if (!(vw[k] & 0x7fffu)) x0 = 0.f;                     // V is post-ReLU: zero <=> inactive
-          if (!(vw[k] & 0x7fff0000u)) x1 = 0.f;
+          const int c = 8 * j + 2 * k, pr = 4 * (j & 1) + k;
+          float x0 = fmaf(gx, c_bw_wrgb[c], fmaf(gy, c_bw_wrgb[128 + c], gz * c_bw_wrgb[256 + c]));
+          float x1 = fmaf(gx, c_bw_wrgb[c + 1], fmaf(gy, c_bw_wrgb[129 + c], gz * c_bw_wrgb[257 + c]));
+          if (!((bits16 >> pr) & 1u)) x0 = 0.f;
+          if (!((bits16 >> (8 + pr)) & 1u)) x1 = 0.f;
           head[4 * j + k] = pack_f16x2(x0, x1, false);
         }
       }
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const _
       if (!tile_valid(round, t)) return make_uint4(0, 0, 0, 0);
       return __ldg(reinterpret_cast<const uint4*>(P.st_m + ((size_t)plane * P.n + sample_index(round, t)) * 8) + (g ^ t));
     };
-    if (n_rounds > 0) build_head(0);
+    if (n_rounds > 0) { prefetch_head(0); build_head(); }
 
     // Column ownership: for tile t this thread drains columns [(g ^ t) * 128, +128) = A k-blocks 2(g^t), 2(g^t)+1 of its
     // row in every step.  The warpgroup that builds the head of tile t (g == t) is therefore the one that owns k-blocks
@@ -351,7 +359,8 @@ __global__ void __launch_bounds__(BwCfg<kPair>::THREADS, 1) k_mlp_tc_bwd(const _
           }
           if (t == 0 && ew == 0 && lane == 0) BW_TRACE(1, 2, nstep);
         }
-        if (b == 4 && round + 1 < n_rounds) build_head(round + 1);
+        if (b == 1 && round + 1 < n_rounds) prefetch_head(round + 1);
+        if (b == 4 && round + 1 < n_rounds) build_head();
       }
     }
   }
@@ -546,7 +555,7 @@ int nm_tc_backward(nm_ctx* ctx, NmNet& net, const float* d_raw, const float* sca
   P.d_raw = d_raw; P.scale = scale;
   P.w_alpha = net.f32 + net.o_alpha_w;
   NM_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_bw_wrgb, net.bw_wrgb, 384 * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
-  P.st_v = st_v; P.st_m = st_m;
+  P.st_m = st_m;
   P.g_pre = g_pre; P.g_f = g_f; P.g_v = g_v;
   P.n = n;
   P.n_tiles = (n + 128 * kpair - 1) / (128 * kpair);

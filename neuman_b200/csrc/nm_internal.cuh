@@ -135,7 +135,7 @@ struct NmTrainStash {
   __half* x;     // [8][n][256] post-ReLU outputs of pts_linears 0..7
   __half* f;     // [n][256]    feature_linear output
   __half* v;     // [n][128]    views layer post-ReLU
-  uint32_t* m;   // [8][n][8]   ReLU sign words of pts_linears 0..7 (16 bits per 16 columns, see mlp_tc.cu epi_sub16)
+  uint32_t* m;   // [9][n][8]   ReLU sign words: planes 0..7 pts_linears, plane 8 views layer (16 bits per 16 columns, mlp_tc.cu epi_sub16)
 };
 int nm_impl_pe_backward(nm_ctx* ctx, const NmNet& net, int which, const float* x, int64_t group, const float* d_enc, int ld,
                         const float* inv_scale, int64_t n, float* d_x, cudaStream_t st);
