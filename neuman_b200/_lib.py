@@ -130,6 +130,7 @@ class Context:
         self.slot_keys = [None] * NM_MAX_NET_SLOTS
         self.slot_clock = 0
         self.slot_used = [0] * NM_MAX_NET_SLOTS
+        self.finalized_uids = set()   # modules with a weakref.finalize hook registered for this ctx
 
     @classmethod
     def get(cls, device):
@@ -137,6 +138,11 @@ class Context:
         if d not in cls._by_device:
             cls._by_device[d] = cls(d)
         return cls._by_device[d]
+
+    def stream(self):
+        """The caller's current torch stream on THIS ctx's device (not the thread's current device)."""
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def check(self, rc):
         if rc != 0:

@@ -7,7 +7,7 @@ import os
 import torch
 
 from . import ops
-from .ops import _ctx_for, _f32, _p, _stream
+from .ops import _ctx_for, _f32, _p
 
 
 class _Raw2Outputs(torch.autograd.Function):
@@ -35,7 +35,7 @@ class _Raw2Outputs(torch.autograd.Function):
         g_rgb, g_acc, g_w, g_depth = opt(g_rgb), opt(g_acc), opt(g_w), opt(g_depth)
         ctx.check(ctx.lib.nm_raw2outputs_backward(ctx.h, _p(r), _p(z), _p(d), R, S, _p(nz if fctx.has_noise else None),
                                                   fctx.sigma_scale, int(fctx.white_bkg), _p(g_rgb), _p(g_depth), _p(g_acc),
-                                                  _p(g_w), _p(grad_raw), _stream()))
+                                                  _p(g_w), _p(grad_raw), ctx.stream()))
         return grad_raw, None, None, None, None, None
 
 
@@ -94,7 +94,7 @@ class _JoinerMLP(torch.autograd.Function):
         raw = torch.empty(n, 4, device=dev, dtype=torch.float32)
         if n:
             ctx.check(ctx.lib.nm_mlp_forward_train(ctx.h, slot, _p(pts), _p(views), n, 0, _p(raw), _p(sx), _p(sf), _p(sv),
-                                                   _p(sm), _stream()))
+                                                   _p(sm), ctx.stream()))
         fctx.joiner = joiner
         fctx.stash = (sx, sf, sv, sm)
         fctx.save_for_backward(pts, views, *params)
@@ -142,7 +142,7 @@ def _input_grad(joiner, P, x, which, terms, inv):
         d_enc = t if d_enc is None else d_enc + t
     n = x.shape[0]
     d_x = torch.empty(n, 3, device=x.device, dtype=torch.float32)
-    ctx.check(ctx.lib.nm_pe_backward(ctx.h, slot, which, _p(x), 0, _p(d_enc), ld, _p(inv.contiguous()), n, _p(d_x), _stream()))
+    ctx.check(ctx.lib.nm_pe_backward(ctx.h, slot, which, _p(x), 0, _p(d_enc), ld, _p(inv.contiguous()), n, _p(d_x), ctx.stream()))
     return d_x
 
 
@@ -150,7 +150,7 @@ def _colsum(ctx, t):
     """[planes, n, width] fp16 -> [planes, width] fp32 column sums (csrc/mlp_tc_bwd.cu: k_colsum_f16)."""
     planes, n, width = t.shape
     out = torch.empty(planes, width, device=t.device, dtype=torch.float32)
-    ctx.check(ctx.lib.nm_colsum_f16(ctx.h, _p(t), planes, n, width, _p(out), _stream()))
+    ctx.check(ctx.lib.nm_colsum_f16(ctx.h, _p(t), planes, n, width, _p(out), ctx.stream()))
     return out
 
 
@@ -161,8 +161,8 @@ def _encodings(joiner, pts, views):
     n = pts.shape[0]
     spe = torch.empty(n, 64, device=pts.device, dtype=torch.float16)
     sdpe = torch.empty(n, 32, device=pts.device, dtype=torch.float16)
-    ctx.check(ctx.lib.nm_encode_f16(ctx.h, slot, 0, _p(pts), 0, n, _p(spe), _stream()))
-    ctx.check(ctx.lib.nm_encode_f16(ctx.h, slot, 1, _p(views), 0, n, _p(sdpe), _stream()))
+    ctx.check(ctx.lib.nm_encode_f16(ctx.h, slot, 0, _p(pts), 0, n, _p(spe), ctx.stream()))
+    ctx.check(ctx.lib.nm_encode_f16(ctx.h, slot, 1, _p(views), 0, n, _p(sdpe), ctx.stream()))
     return spe, sdpe
 
 
@@ -200,7 +200,7 @@ def _weight_grads(joiner, stash, pts, views, g, g_pre, g_f, g_v, inv):
     else:                                                                 # k_dw_gemm: every plane read once at HBM rate
         dw = torch.empty(9, 256, 256, device=g.device, dtype=torch.float32)
         db = torch.empty(9, 256, device=g.device, dtype=torch.float32)
-        ctx.check(ctx.lib.nm_dw_gemm(ctx.h, _p(g_pre), _p(g_f), _p(g_v), _p(sx), _p(sf), g.shape[0], _p(dw), _p(db), _stream()))
+        ctx.check(ctx.lib.nm_dw_gemm(ctx.h, _p(g_pre), _p(g_f), _p(g_v), _p(sx), _p(sf), g.shape[0], _p(dw), _p(db), ctx.stream()))
     dw, db = dw * inv, db * inv
     grads['views_linears.0.weight'] = torch.cat([dw[8, :128], wd[:, :n_dpe]], 1)
     grads['views_linears.0.bias'] = db[8, :128]
@@ -226,7 +226,7 @@ def _chain_kernel(joiner, P, stash, g):
     h = dict(device=g.device, dtype=torch.float16)
     g_pre, g_f, g_v = torch.empty(8, n, 256, **h), torch.empty(n, 256, **h), torch.empty(n, 128, **h)
     ctx.check(ctx.lib.nm_mlp_backward(ctx.h, slot, _p(g), _p(scale), n, _p(sv), _p(sm), _p(g_pre), _p(g_f), _p(g_v),
-                                      _stream()))
+                                      ctx.stream()))
     return g_pre, g_f, g_v, 1.0 / scale
 
 

@@ -48,7 +48,7 @@ static void free_mesh(NmMesh& m) {
 }
 
 extern "C" int nm_ctx_destroy(nm_ctx* ctx) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (auto& n : ctx->nets) free_net(n);
@@ -66,7 +66,7 @@ extern "C" const char* nm_last_error(const nm_ctx* ctx) { return ctx ? ctx->err.
 extern "C" int64_t nm_launch_count(const nm_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int nm_profile_enable(nm_ctx* ctx, int32_t on) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   ctx->profile = on != 0;
   ctx->prof_used = 0;
   ctx->prof_evals = 0;
@@ -74,7 +74,7 @@ extern "C" int nm_profile_enable(nm_ctx* ctx, int32_t on) {
 }
 
 extern "C" int nm_profile_read(nm_ctx* ctx, double* mlp_ms, int64_t* mlp_launches, int64_t* mlp_evals) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   double total = 0.0;
   for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
     NM_CHECK_CUDA(ctx, cudaEventSynchronize(ctx->prof_events[i + 1]));
@@ -89,7 +89,7 @@ extern "C" int nm_profile_read(nm_ctx* ctx, double* mlp_ms, int64_t* mlp_launche
 }
 
 extern "C" int nm_last_render_stats(const nm_ctx* ctx, int64_t* mlp_evals, int64_t* hit_rays) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (mlp_evals) *mlp_evals = ctx->last_mlp_evals;
   if (hit_rays) *hit_rays = ctx->last_hit_rays;
   return NM_OK;
@@ -174,7 +174,7 @@ static void pe_cycles_table(int kind, float fmin, float fmax, int nf, std::vecto
 }
 
 extern "C" int nm_net_pack(nm_ctx* ctx, int slot, const nm_nerf_desc* d, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (slot < 0 || slot >= NM_MAX_NET_SLOTS || !d) NM_FAIL(ctx, NM_ERR_INVALID, "nm_net_pack: bad slot/desc");
   if (d->pos_n_freqs != 10 || d->dir_n_freqs != 4)
     NM_FAIL(ctx, NM_ERR_UNSUPPORTED, "nm_net_pack: only pos_N_freqs=10 / dir_N_freqs=4 (63/27-d encodings) is built");
@@ -295,7 +295,7 @@ static int mlp_dispatch(nm_ctx* ctx, int slot, int mode, const float* pts, const
 
 extern "C" int nm_mlp_forward(nm_ctx* ctx, int slot, int mode, const float* pts, const float* views, int64_t n,
                               int32_t views_per_ray, float* raw, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (!pts || !views || views_per_ray < 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward: null pts/views");
   if (views_per_ray > 0 && n % views_per_ray != 0)
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward: n is not a multiple of views_per_ray");
@@ -305,7 +305,7 @@ extern "C" int nm_mlp_forward(nm_ctx* ctx, int slot, int mode, const float* pts,
 extern "C" int nm_mlp_forward_train(nm_ctx* ctx, int slot, const float* pts, const float* views, int64_t n,
                                     int32_t views_per_ray, float* raw, void* stash_x, void* stash_f, void* stash_v,
                                     void* stash_m, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (!pts || !views || views_per_ray < 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward_train: null pts/views");
   if (!stash_x || !stash_f || !stash_v || !stash_m)
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward_train: null stash");
@@ -317,7 +317,7 @@ extern "C" int nm_mlp_forward_train(nm_ctx* ctx, int slot, const float* pts, con
 
 extern "C" int nm_mlp_backward(nm_ctx* ctx, int slot, const float* d_raw, const float* loss_scale, int64_t n,
                                const void* stash_v, const void* stash_m, void* g_pre, void* g_f, void* g_v, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (slot < 0 || slot >= NM_MAX_NET_SLOTS || !ctx->nets[slot].packed)
     NM_FAIL(ctx, NM_ERR_STATE, "nm_mlp_backward: net slot not packed");
   if (n < 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_backward: bad argument");
@@ -330,7 +330,7 @@ extern "C" int nm_mlp_backward(nm_ctx* ctx, int slot, const float* d_raw, const 
 
 extern "C" int nm_encode_f16(nm_ctx* ctx, int slot, int32_t which, const float* x, int64_t group, int64_t n, void* out,
                              void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (slot < 0 || slot >= NM_MAX_NET_SLOTS || !ctx->nets[slot].packed)
     NM_FAIL(ctx, NM_ERR_STATE, "nm_encode_f16: net slot not packed");
   if ((which != 0 && which != 1) || n < 0 || group < 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_encode_f16: bad argument");
@@ -341,7 +341,7 @@ extern "C" int nm_encode_f16(nm_ctx* ctx, int slot, int32_t which, const float* 
 
 extern "C" int nm_pe_backward(nm_ctx* ctx, int slot, int32_t which, const float* x, int64_t group, const float* d_enc,
                               int32_t ld, const float* inv_scale, int64_t n, float* d_x, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (slot < 0 || slot >= NM_MAX_NET_SLOTS || !ctx->nets[slot].packed)
     NM_FAIL(ctx, NM_ERR_STATE, "nm_pe_backward: net slot not packed");
   if ((which != 0 && which != 1) || n < 0 || group < 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_pe_backward: bad argument");
@@ -355,7 +355,7 @@ extern "C" int nm_pe_backward(nm_ctx* ctx, int slot, int32_t which, const float*
 
 extern "C" int nm_dw_gemm(nm_ctx* ctx, const void* g_pre, const void* g_f, const void* g_v, const void* stash_x,
                           const void* stash_f, int64_t n, float* out, float* bias_out, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (n < 0 || !out || !bias_out) NM_FAIL(ctx, NM_ERR_INVALID, "nm_dw_gemm: bad argument");
   if (n == 0) {
     NM_CHECK_CUDA(ctx, cudaMemsetAsync(out, 0, (size_t)9 * 256 * 256 * sizeof(float), (cudaStream_t)stream));
@@ -368,7 +368,7 @@ extern "C" int nm_dw_gemm(nm_ctx* ctx, const void* g_pre, const void* g_f, const
 }
 
 extern "C" int nm_colsum_f16(nm_ctx* ctx, const void* src, int32_t planes, int64_t n, int32_t width, float* out, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (planes < 0 || n < 0 || width <= 0 || width > 256 || (width & 1)) NM_FAIL(ctx, NM_ERR_INVALID, "nm_colsum_f16: bad shape");
   if (planes == 0) return NM_OK;
   if (!out || (n > 0 && !src)) NM_FAIL(ctx, NM_ERR_INVALID, "nm_colsum_f16: null argument");
@@ -377,7 +377,7 @@ extern "C" int nm_colsum_f16(nm_ctx* ctx, const void* src, int32_t planes, int64
 
 extern "C" int nm_mlp_forward_rays(nm_ctx* ctx, int slot, int mode, const float* origins, const float* dirs,
                                    const float* z, int64_t R, int32_t S, float* raw, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (!origins || !dirs || !z || S <= 0 || R < 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward_rays: bad argument");
   return mlp_dispatch(ctx, slot, mode, nullptr, nullptr, origins, dirs, z, R * (int64_t)S, S, raw, stream);
 }

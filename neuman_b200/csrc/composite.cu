@@ -95,7 +95,7 @@ int nm_impl_raw2outputs_zend(nm_ctx* ctx, const float* raw, const float* z, cons
 extern "C" int nm_raw2outputs(nm_ctx* ctx, const float* raw, const float* z, const float* rays_d, int64_t R,
                               int32_t S, const float* noise, float sigma_scale, int32_t white_bkg, float* rgb,
                               float* disp, float* acc, float* weights, float* depth, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (R == 0) return NM_OK;
   if (!raw || !z || !rays_d || R < 0 || S <= 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_raw2outputs: bad argument");
   unsigned blocks = (unsigned)((R * 32 + 255) / 256);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(32 * MERGE_WARPS) k_merge(MergeParams p, long 
 extern "C" int nm_merge_samples(nm_ctx* ctx, int32_t n_lists, const float* const* z_lists,
                                 const float* const* raw_lists, const int32_t* S_list, int64_t R, float* z_out,
                                 float* raw_out, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (R == 0) return NM_OK;
   if (n_lists < 1 || n_lists > 1 + NM_MAX_ACTORS || !z_lists || !S_list || !z_out || R < 0)
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_merge_samples: bad argument");
@@ -273,7 +273,7 @@ extern "C" int nm_raw2outputs_backward(nm_ctx* ctx, const float* raw, const floa
                                        int32_t S, const float* noise, float sigma_scale, int32_t white_bkg,
                                        const float* grad_rgb, const float* grad_depth, const float* grad_acc,
                                        const float* grad_weights, float* grad_raw, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (R == 0) return NM_OK;
   if (!raw || !z || !rays_d || !grad_raw || R < 0 || S <= 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_raw2outputs_backward: bad argument");
   char* ws;

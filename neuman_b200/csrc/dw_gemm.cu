@@ -270,11 +270,7 @@ int nm_impl_dw_gemm(nm_ctx* ctx, const __half* g_pre, const __half* g_f, const _
     }
   }
   P.n_work = w;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NM_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_dw_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  NM_SET_SMEM_ONCE(ctx, (k_dw_gemm), DwCfg::SMEM_BYTES);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * w);
   cfg.blockDim = dim3(DW_THREADS);

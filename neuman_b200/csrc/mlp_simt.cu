@@ -170,11 +170,7 @@ int nm_simt_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float
   P.dir_pe = {net.desc.dir_pe_kind, net.desc.dir_n_freqs, net.f32 + net.o_dir_bv};
   NmMlpInput in{pts, views, origins, dirs, z, (long long)n, group};
   size_t smem = (size_t)(2 * TM * 256 + TM * 64 + TM * 32 + TM) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NM_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_mlp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  NM_SET_SMEM_ONCE(ctx, (k_mlp_simt), (int)smem);
   unsigned blocks = (unsigned)((n + TM - 1) / TM);
   k_mlp_simt<<<blocks, NT, smem, st>>>(P, in, raw);
   NM_CHECK_LAUNCH(ctx);

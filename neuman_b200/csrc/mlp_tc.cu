@@ -717,11 +717,7 @@ int nm_tc_pack(nm_ctx* ctx, NmNet& net, cudaStream_t st) {
 template <int kPair, bool kConst, bool kTrain>
 static int launch_tc(nm_ctx* ctx, const TcParams& P, cudaStream_t st) {
   using C = TcCfg<kPair>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NM_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_mlp_tc<kPair, kConst, kTrain>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  NM_SET_SMEM_ONCE(ctx, (k_mlp_tc<kPair, kConst, kTrain>), C::SMEM_BYTES);
   int ctas = ctx->sm_count - (ctx->sm_count % kPair);
   long long need = P.n_tiles * kPair;                       // CTAs that have work in the first round
   need = (need + C::NT - 1) / C::NT;

@@ -518,11 +518,7 @@ int nm_tc_pack_bwd(nm_ctx* ctx, NmNet& net, cudaStream_t st) {
 template <int kPair>
 static int launch_bwd(nm_ctx* ctx, const BwParams& P, cudaStream_t st) {
   using C = BwCfg<kPair>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NM_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_mlp_tc_bwd<kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  NM_SET_SMEM_ONCE(ctx, (k_mlp_tc_bwd<kPair>), C::SMEM_BYTES);
   int ctas = ctx->sm_count - (ctx->sm_count % kPair);
   long long need = (P.n_tiles * kPair + C::NT - 1) / C::NT;
   if (need < ctas) ctas = (int)((need + kPair - 1) / kPair * kPair);

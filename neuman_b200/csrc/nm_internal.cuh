@@ -84,6 +84,34 @@ struct nm_ctx {
   size_t can64_cap = 0;
 };
 
+// Every C entry point runs on the ctx's device whatever device the calling thread has current (a process may hold
+// one ctx per GPU); the previous device is restored on return.
+struct NmDeviceGuard {
+  int prev = -1;
+  explicit NmDeviceGuard(const nm_ctx* ctx) {
+    int cur = -1;
+    if (ctx && cudaGetDevice(&cur) == cudaSuccess && cur != ctx->device) {
+      prev = cur;
+      cudaSetDevice(ctx->device);
+    }
+  }
+  ~NmDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define NM_ENTER(ctx)                       \
+  if (!(ctx)) return NM_ERR_INVALID;        \
+  NmDeviceGuard _nm_guard(ctx)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember which devices a kernel was prepared on
+#define NM_SET_SMEM_ONCE(ctx, kernel, bytes)                                                                  \
+  do {                                                                                                        \
+    static unsigned long long _done = 0ull;                                                                   \
+    const unsigned long long _bit = 1ull << ((ctx)->device & 63);                                             \
+    if (!(_done & _bit)) {                                                                                    \
+      NM_CHECK_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes))); \
+      _done |= _bit;                                                                                          \
+    }                                                                                                         \
+  } while (0)
+
 #define NM_CHECK_CUDA(ctx, call)                                                         \
   do {                                                                                   \
     cudaError_t _e = (call);                                                             \

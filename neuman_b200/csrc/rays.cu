@@ -67,7 +67,7 @@ static void invert3x3(const double* m, double* o) {
 
 extern "C" int nm_raygen(nm_ctx* ctx, const nm_camera* cam, int mode, int64_t pix0, int64_t n,
                          const int32_t* xy, float* origins, float* dirs, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (n == 0) return NM_OK;
   if (!cam || !origins || !dirs || n < 0 || (mode != 0 && mode != 1))
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_raygen: bad argument");
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) k_near_far(const float* __restrict__ orig
 extern "C" int nm_near_far(nm_ctx* ctx, const float* origins, const float* dirs, int64_t R,
                            const float* verts, int32_t n_verts, float geo_threshold, float* near_out,
                            float* far_out, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (R == 0) return NM_OK;
   if (!origins || !dirs || !verts || !near_out || !far_out || R < 0 || n_verts < 0)
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_near_far: bad argument");
@@ -246,7 +246,7 @@ extern "C" int nm_ray_to_samples(nm_ctx* ctx, const float* origins, const float*
                                  const float* far_v, float near_s, float far_s, int64_t R, int32_t S,
                                  int32_t lindisp, const float* t_rand, float* pts, float* dirs_out, float* z,
                                  void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (R == 0) return NM_OK;
   if (R < 0 || S <= 0 || ((pts || dirs_out) && (!origins || !dirs)))
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_ray_to_samples: bad argument");

@@ -149,7 +149,7 @@ int copy_out(nm_ctx* ctx, float* dst, const float* src, size_t n, int host_out, 
 extern "C" int nm_render_vanilla(nm_ctx* ctx, int coarse_slot, int fine_slot, const nm_camera* cam,
                                  const nm_render_opts* opt, int64_t pix0, int64_t n, float* rgb, float* depth,
                                  int32_t host_out, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   TRY(check_common(ctx, cam, opt, pix0, n, "nm_render_vanilla"));
   if (!slot_ok(ctx, coarse_slot) || (fine_slot >= 0 && !slot_ok(ctx, fine_slot)))
     NM_FAIL(ctx, NM_ERR_STATE, "nm_render_vanilla: net slot not packed");
@@ -216,7 +216,7 @@ static int compact(nm_ctx* ctx, const float* near_v, const float* far_v, int64_t
 extern "C" int nm_render_smpl_nerf(nm_ctx* ctx, int human_slot, int actor, const nm_camera* cam,
                                    const nm_render_opts* opt, int64_t pix0, int64_t n, float* rgb, float* depth,
                                    float* acc, int32_t host_out, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   TRY(check_common(ctx, cam, opt, pix0, n, "nm_render_smpl_nerf"));
   if (!slot_ok(ctx, human_slot)) NM_FAIL(ctx, NM_ERR_STATE, "nm_render_smpl_nerf: net slot not packed");
   if (actor < 0 || actor >= NM_MAX_ACTORS || !ctx->meshes[actor].set)
@@ -276,7 +276,7 @@ extern "C" int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int
                                 const int32_t* human_slots, const int32_t* actors, int32_t multi_person,
                                 const nm_camera* cam, const nm_render_opts* opt, int64_t pix0, int64_t n, float* rgb,
                                 float* depth, float* acc, int32_t host_out, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   TRY(check_common(ctx, cam, opt, pix0, n, "nm_render_hybrid"));
   if (!slot_ok(ctx, coarse_slot) || (fine_slot >= 0 && !slot_ok(ctx, fine_slot)))
     NM_FAIL(ctx, NM_ERR_STATE, "nm_render_hybrid: bkg net slot not packed");

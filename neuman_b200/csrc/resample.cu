@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_sample_pdf(const float* __res
 
 extern "C" int nm_sample_pdf(nm_ctx* ctx, const float* bins, const float* weights, int64_t R, int32_t B, int32_t N,
                              const float* u, float* out, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (R == 0) return NM_OK;
   if (!bins || !weights || !out || R < 0 || B < 2 || N <= 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_sample_pdf: bad argument");
   size_t smem = (size_t)RS_WARPS * 2 * B * sizeof(float);
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_importance(
 extern "C" int nm_importance_samples(nm_ctx* ctx, const float* origins, const float* dirs, const float* z,
                                      const float* weights, int64_t R, int32_t S, int32_t N, int32_t including_old,
                                      float* pts, float* dirs_out, float* z_out, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (R == 0) return NM_OK;
   if (!z || !weights || !z_out || R < 0 || S < 3 || N <= 0 || ((pts || dirs_out) && (!origins || !dirs)))
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_importance_samples: bad argument (needs S >= 3)");

@@ -138,7 +138,7 @@ static int check_model(nm_ctx* ctx, const nm_smpl_model* m) {
 
 extern "C" int nm_smpl_vertex_transforms(nm_ctx* ctx, const nm_smpl_model* m, const float* pose, const float* betas,
                                          int32_t concat_joints, float* T, float* verts, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   int rc = check_model(ctx, m);
   if (rc) return rc;
   if (!pose || !betas || !T) NM_FAIL(ctx, NM_ERR_INVALID, "nm_smpl_vertex_transforms: null argument");
@@ -213,7 +213,7 @@ __global__ void k_smpl_scene(const float* __restrict__ T_pose, const float* __re
 extern "C" int nm_smpl_scene_transforms(nm_ctx* ctx, const nm_smpl_model* m, const float* pose, const float* da_pose,
                                         const float* betas, const double* alignment, double scale, double* T_da2scene,
                                         float* world_verts, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   int rc = check_model(ctx, m);
   if (rc) return rc;
   if (!pose || !da_pose || !betas || !alignment || !T_da2scene)
@@ -221,16 +221,21 @@ extern "C" int nm_smpl_scene_transforms(nm_ctx* ctx, const nm_smpl_model* m, con
   cudaStream_t st = (cudaStream_t)stream;
   const int nv = m->n_verts, nj = m->n_joints, total = nv + nj;
   char* ws;
-  size_t floats = (size_t)total * 3 + nj * 3 + 2 * nj * 16 + (size_t)2 * total * 16 + 1024;
-  if ((rc = nm_impl_workspace(ctx, floats * sizeof(float) + 4096, &ws))) return rc;
+  // the same rounding as `take` below, buffer by buffer: v_shaped, J, A, T_pose, T_da, rest
+  auto pad64 = [](size_t n) { return (n + 63) & ~size_t(63); };
+  const size_t floats = pad64((size_t)nv * 3) + pad64((size_t)nj * 3) + pad64((size_t)nj * 16) +
+                        2 * pad64((size_t)total * 16) + pad64((size_t)total * 3);
+  if ((rc = nm_impl_workspace(ctx, floats * sizeof(float), &ws))) return rc;
   float* p = reinterpret_cast<float*>(ws);
-  auto take = [&](size_t n) { float* r = p; p += (n + 63) & ~size_t(63); return r; };
+  auto take = [&](size_t n) { float* r = p; p += pad64(n); return r; };
   float* v_shaped = take((size_t)nv * 3);
   float* J = take(nj * 3);
   float* A = take(nj * 16);
   float* T_pose = take((size_t)total * 16);
   float* T_da = take((size_t)total * 16);
   float* rest = take((size_t)total * 3);
+  if ((size_t)(reinterpret_cast<char*>(p) - ws) > ctx->ws_bytes)
+    NM_FAIL(ctx, NM_ERR_STATE, "nm_smpl_scene_transforms: workspace overflow (internal sizing bug)");
   if ((rc = smpl_lbs(ctx, m, pose, betas, 1, v_shaped, J, A, T_pose, nullptr, st))) return rc;
   if ((rc = smpl_lbs(ctx, m, da_pose, betas, 1, v_shaped, J, A, T_da, rest, st))) return rc;
   Mat4d pre;   // S . align^T  (s = eye; s[:3,:3] *= scale; T = s @ (alignment.T @ T_da2pose), :318-321)

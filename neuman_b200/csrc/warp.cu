@@ -345,7 +345,7 @@ static BvhView bvh_view(const NmMesh& m) {
 
 extern "C" int nm_mesh_set(nm_ctx* ctx, int actor, const float* verts, int32_t n_verts, const int32_t* faces,
                            int32_t n_faces, const double* T, int32_t n_T, int32_t on_device, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (actor < 0 || actor >= NM_MAX_ACTORS || !verts || !faces || n_verts <= 0 || n_faces <= 0 || (T && n_T < n_verts))
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_mesh_set: bad argument (need n_T >= n_verts)");
   if (!T) n_T = 0;                                   // distance queries only (nm_signed_distance)
@@ -407,7 +407,7 @@ extern "C" int nm_mesh_set(nm_ctx* ctx, int actor, const float* verts, int32_t n
 
 extern "C" int nm_warp_to_canonical(nm_ctx* ctx, int actor, const float* pts, int64_t R, int32_t S, float* can_pts,
                                     float* can_dirs, float* closest, int32_t* face_id, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (R == 0) return NM_OK;
   if (actor < 0 || actor >= NM_MAX_ACTORS || !ctx->meshes[actor].set || !ctx->meshes[actor].has_T)
     NM_FAIL(ctx, NM_ERR_STATE, "nm_warp_to_canonical: mesh (with per-vertex transforms) not set");
@@ -552,7 +552,7 @@ static int build_pseudonormals(nm_ctx* ctx, NmMesh& m, cudaStream_t st) {
 }
 
 extern "C" int nm_signed_distance(nm_ctx* ctx, int actor, const float* pts, int64_t n, double* S, int32_t* I, double* C, void* stream) {
-  if (!ctx) return NM_ERR_INVALID;
+  NM_ENTER(ctx);
   if (n == 0) return NM_OK;
   if (actor < 0 || actor >= NM_MAX_ACTORS || !ctx->meshes[actor].set) NM_FAIL(ctx, NM_ERR_STATE, "nm_signed_distance: mesh not set");
   if (!pts || n < 0) NM_FAIL(ctx, NM_ERR_INVALID, "nm_signed_distance: bad argument");

@@ -3,7 +3,9 @@
 device; every function fails loudly otherwise -- there is no CPU path in this package.
 """
 import ctypes as C
+import itertools
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -24,10 +26,6 @@ def _ctx_for(t):
     return Context.get(t.device.index if t.device.index is not None else torch.cuda.current_device())
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-
 def _f32(t, device=None):
     if not isinstance(t, torch.Tensor):
         t = torch.as_tensor(np.asarray(t))
@@ -46,13 +44,44 @@ def _p(t):
 _PE_KIND = {"posenc": _lib.NM_PE_POSENC, "rotate": _lib.NM_PE_ROTATE}
 
 
+_uid_counter = itertools.count(1)
+
+
+def _net_uid(joiner):
+    """Process-unique id of a Joiner, assigned at its first pack.  (id() is reused by CPython after garbage collection,
+    and the caching allocator hands a new net the same storage with _version 0: an id()-based key then matches
+    the dead net's slot.)"""
+    tag = joiner.__dict__.get("_nm_uid")
+    if tag is None or tag[1] != id(joiner):         # never packed, or a copy.deepcopy that inherited the attribute
+        tag = (next(_uid_counter), id(joiner))
+        joiner.__dict__["_nm_uid"] = tag
+    return tag[0]
+
+
 def _net_key(joiner):
-    ps = list(joiner.nerf.parameters())
-    return (id(joiner),) + tuple((p.data_ptr(), p._version) for p in ps)
+    # (data_ptr, _version) per parameter detects in-place updates and `.data = ...` swaps to other storage
+    return (_net_uid(joiner),) + tuple((p.data_ptr(), p._version) for p in joiner.nerf.parameters())
+
+
+def _evict_uid(ctx_ref, uid):
+    ctx = ctx_ref()
+    if ctx is None:
+        return
+    for k in [k for k in ctx.slots if k[0] == uid]:
+        ctx.slot_keys[ctx.slots.pop(k)] = None
+
+
+def invalidate_net(joiner):
+    """Forget the packed copy of `joiner` on every device (call after replacing parameter storage in a way that
+    keeps data_ptr and _version, e.g. `p.data.copy_()` through a non-tracking view)."""
+    tag = joiner.__dict__.get("_nm_uid")
+    if tag is not None:
+        for ctx in list(Context._by_device.values()):
+            _evict_uid(weakref.ref(ctx), tag[0])
 
 
 def net_slot(joiner, ctx=None):
-    """Packs (lazily, keyed on parameter storage + version) a Joiner into a library slot."""
+    """Packs (lazily, keyed on a per-module uid + parameter storage + version) a Joiner into a library slot."""
     nerf = joiner.nerf
     p0 = nerf.pts_linears[0].weight
     ctx = ctx or _ctx_for(p0)
@@ -67,8 +96,11 @@ def net_slot(joiner, ctx=None):
     if len(nerf.pts_linears) != 8 or nerf.pts_linears[1].weight.shape != (256, 256) or tuple(nerf.skips) != (4,):
         raise NotImplementedError("only the 8x256, skips=[4] architecture is built (reference default)")
     # stale entries of the same module
-    for k in [k for k in ctx.slots if k[0] == id(joiner)]:
-        ctx.slot_keys[ctx.slots.pop(k)] = None
+    uid = key[0]
+    _evict_uid(weakref.ref(ctx), uid)
+    if uid not in ctx.finalized_uids:                                # release the slot when the module is garbage-collected
+        ctx.finalized_uids.add(uid)
+        weakref.finalize(joiner, _evict_uid, weakref.ref(ctx), uid)
     free = [i for i, k in enumerate(ctx.slot_keys) if k is None]
     if free:
         s = free[0]
@@ -94,9 +126,9 @@ def net_slot(joiner, ctx=None):
     d.pos_pe_kind, d.dir_pe_kind = _PE_KIND[pp.mapping], _PE_KIND[dp.mapping]
     d.pos_min_freq, d.pos_max_freq, d.pos_n_freqs = float(pp.min_freq), float(pp.max_freq), int(pp.N_freqs)
     d.dir_min_freq, d.dir_max_freq, d.dir_n_freqs = float(dp.min_freq), float(dp.max_freq), int(dp.N_freqs)
-    ctx.check(ctx.lib.nm_net_pack(ctx.h, s, C.byref(d), _stream()))
+    ctx.check(ctx.lib.nm_net_pack(ctx.h, s, C.byref(d), ctx.stream()))
     if keep:
-        torch.cuda.current_stream().synchronize()  # `keep` temporaries may be freed after this
+        torch.cuda.current_stream(ctx.device).synchronize()  # `keep` temporaries may be freed after this
     ctx.slots[key] = s
     ctx.slot_keys[s] = key
     ctx.slot_clock += 1
@@ -116,7 +148,7 @@ def joiner_forward(joiner, input_pts, input_views=None, mode=None):
     assert views.shape[0] == pts.shape[0], "input_views must match input_pts"
     raw = torch.empty(pts.shape[0], 4, device=pts.device, dtype=torch.float32)
     ctx.check(ctx.lib.nm_mlp_forward(ctx.h, slot, _mlp_mode() if mode is None else mode, _p(pts), _p(views),
-                                     pts.shape[0], 0, _p(raw), _stream()))
+                                     pts.shape[0], 0, _p(raw), ctx.stream()))
     return raw.reshape(*shape, 4)
 
 
@@ -128,7 +160,7 @@ def mlp_forward_rays(joiner, origins, dirs, z_vals, mode=None):
     R, S = z.shape
     raw = torch.empty(R, S, 4, device=z.device, dtype=torch.float32)
     ctx.check(ctx.lib.nm_mlp_forward_rays(ctx.h, slot, _mlp_mode() if mode is None else mode, _p(o), _p(d), _p(z), R, S,
-                                          _p(raw), _stream()))
+                                          _p(raw), ctx.stream()))
     return raw
 
 
@@ -163,7 +195,7 @@ def shot_rays(cap, xys, device=None):
     d = torch.empty(n, 3, device=device)
     cam = camera_struct(cap)
     with torch.cuda.device(device):
-        ctx.check(ctx.lib.nm_raygen(ctx.h, C.byref(cam), 0, 0, n, _p(xy), _p(o), _p(d), _stream()))
+        ctx.check(ctx.lib.nm_raygen(ctx.h, C.byref(cam), 0, 0, n, _p(xy), _p(o), _p(d), ctx.stream()))
     return o, d
 
 
@@ -176,7 +208,7 @@ def shot_all_rays(cap, device=None, mode=1):
     d = torch.empty(n, 3, device=device)
     cam = camera_struct(cap)
     with torch.cuda.device(device):
-        ctx.check(ctx.lib.nm_raygen(ctx.h, C.byref(cam), mode, 0, n, None, _p(o), _p(d), _stream()))
+        ctx.check(ctx.lib.nm_raygen(ctx.h, C.byref(cam), mode, 0, n, None, _p(o), _p(d), ctx.stream()))
     return o, d
 
 
@@ -188,7 +220,7 @@ def geometry_guided_near_far(orig, dir, vert, geo_threshold=DEFAULT_GEO_THRESH):
     near = torch.empty(o.shape[0], device=o.device)
     far = torch.empty(o.shape[0], device=o.device)
     ctx.check(ctx.lib.nm_near_far(ctx.h, _p(o), _p(d), o.shape[0], _p(v), v.shape[0], float(geo_threshold),
-                                  _p(near), _p(far), _stream()))
+                                  _p(near), _p(far), ctx.stream()))
     return near, far
 
 
@@ -211,7 +243,7 @@ def ray_to_samples(ray_batch, samples_per_ray, lindisp=False, perturb=0., device
     if perturb > 0.:
         tr = _f32(t_rand, o.device) if t_rand is not None else torch.rand(R, S, device=o.device)
     ctx.check(ctx.lib.nm_ray_to_samples(ctx.h, _p(o), _p(d), _p(near), _p(far), 0.0, 0.0, R, S, int(bool(lindisp)),
-                                        _p(tr), _p(pts), _p(dirs), _p(z), _stream()))
+                                        _p(tr), _p(pts), _p(dirs), _p(z), ctx.stream()))
     return pts, dirs, z
 
 
@@ -226,7 +258,7 @@ def sample_pdf(bins, weights, N_samples, det=False, device='cuda', u=None):
         u = torch.rand(R, N_samples, device=b.device)
     uu = _f32(u, b.device) if u is not None else None
     out = torch.empty(R, N_samples, device=b.device)
-    ctx.check(ctx.lib.nm_sample_pdf(ctx.h, _p(b), _p(w), R, B, int(N_samples), _p(uu), _p(out), _stream()))
+    ctx.check(ctx.lib.nm_sample_pdf(ctx.h, _p(b), _p(w), R, B, int(N_samples), _p(uu), _p(out), ctx.stream()))
     return out
 
 
@@ -246,7 +278,7 @@ def ray_to_importance_samples(ray_batch, z_vals, weights, importance_samples_per
     dirs = torch.empty(R, total, 3, device=z.device)
     zo = torch.empty(R, total, device=z.device)
     ctx.check(ctx.lib.nm_importance_samples(ctx.h, _p(o), _p(d), _p(z), _p(w), R, S, N, int(bool(including_old)),
-                                            _p(pts), _p(dirs), _p(zo), _stream()))
+                                            _p(pts), _p(dirs), _p(zo), ctx.stream()))
     return pts, dirs, zo
 
 
@@ -264,7 +296,7 @@ def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkg=True, noise=None
     disp, acc, depth = (torch.empty(R, device=r.device) for _ in range(3))
     w = torch.empty(R, S, device=r.device)
     ctx.check(ctx.lib.nm_raw2outputs(ctx.h, _p(r), _p(z), _p(d), R, S, _p(nz), float(sigma_scale), int(bool(white_bkg)),
-                                     _p(rgb), _p(disp), _p(acc), _p(w), _p(depth), _stream()))
+                                     _p(rgb), _p(disp), _p(acc), _p(w), _p(depth), ctx.stream()))
     return rgb, disp, acc, w, depth
 
 
@@ -281,7 +313,7 @@ def merge_samples(z_list, raw_list):
     sp = (C.c_int32 * n)(*S)
     zo = torch.empty(R, sum(S), device=z_list[0].device)
     ro = torch.empty(R, sum(S), 4, device=z_list[0].device)
-    ctx.check(ctx.lib.nm_merge_samples(ctx.h, n, zp, rp, sp, R, _p(zo), _p(ro), _stream()))
+    ctx.check(ctx.lib.nm_merge_samples(ctx.h, n, zp, rp, sp, R, _p(zo), _p(ro), ctx.stream()))
     return zo, ro
 
 
@@ -305,7 +337,7 @@ def set_mesh(verts, faces, T, actor=0, device=None):
             t = t.contiguous().reshape(-1, 16)
         with torch.cuda.device(device):
             ctx.check(ctx.lib.nm_mesh_set(ctx.h, int(actor), _p(v), v.shape[0], _p(f), f.shape[0], _p(t),
-                                          0 if t is None else t.shape[0], 1, _stream()))
+                                          0 if t is None else t.shape[0], 1, ctx.stream()))
         return ctx
     device = torch.device(device or "cuda")
     ctx = Context.get(device.index if device.index is not None else torch.cuda.current_device())
@@ -318,7 +350,7 @@ def set_mesh(verts, faces, T, actor=0, device=None):
         tp, tn = t.ctypes.data_as(C.c_void_p), t.shape[0]
     with torch.cuda.device(device):
         ctx.check(ctx.lib.nm_mesh_set(ctx.h, int(actor), v.ctypes.data_as(C.c_void_p), v.shape[0],
-                                      f.ctypes.data_as(C.c_void_p), f.shape[0], tp, tn, 0, _stream()))
+                                      f.ctypes.data_as(C.c_void_p), f.shape[0], tp, tn, 0, ctx.stream()))
     return ctx
 
 
@@ -340,7 +372,7 @@ def signed_distance(pts, verts, faces, actor=NM_MAX_ACTORS - 1, device=None):
     I = torch.empty(n, device=p.device, dtype=torch.int32)
     Cl = torch.empty(n, 3, device=p.device, dtype=torch.float64)
     with torch.cuda.device(p.device):
-        ctx.check(ctx.lib.nm_signed_distance(ctx.h, int(actor), _p(p), n, _p(S), _p(I), _p(Cl), _stream()))
+        ctx.check(ctx.lib.nm_signed_distance(ctx.h, int(actor), _p(p), n, _p(S), _p(I), _p(Cl), ctx.stream()))
     if as_numpy:
         return S.cpu().numpy(), I.cpu().numpy(), Cl.cpu().numpy()
     return S, I, Cl
@@ -378,7 +410,7 @@ def warp_samples_to_canonical(pts, verts, faces, T, actor=0, return_face_id=Fals
     R, S, _ = p.shape
     cp, cd, cl = (torch.empty(R, S, 3, device=p.device) for _ in range(3))
     fid = torch.empty(R, S, device=p.device, dtype=torch.int32)
-    ctx.check(ctx.lib.nm_warp_to_canonical(ctx.h, int(actor), _p(p), R, S, _p(cp), _p(cd), _p(cl), _p(fid), _stream()))
+    ctx.check(ctx.lib.nm_warp_to_canonical(ctx.h, int(actor), _p(p), R, S, _p(cp), _p(cd), _p(cl), _p(fid), ctx.stream()))
     if return_face_id:
         return cp, cd, cl, fid
     return cp, cd, cl
@@ -421,7 +453,7 @@ def smpl_verts_transformations(model, poses, betas, concat_joints=False):
     verts = torch.empty(n, 3, device=model.device)
     with torch.cuda.device(model.device):
         ctx.check(ctx.lib.nm_smpl_vertex_transforms(ctx.h, C.byref(model.struct), _p(pose), _p(beta), int(bool(concat_joints)),
-                                                    _p(T), _p(verts), _stream()))
+                                                    _p(T), _p(verts), ctx.stream()))
     return verts, T
 
 
@@ -441,7 +473,7 @@ def smpl_scene_transforms(model, pose, betas, alignment, scale):
     world = torch.empty(n, 3, device=model.device)
     with torch.cuda.device(model.device):
         ctx.check(ctx.lib.nm_smpl_scene_transforms(ctx.h, C.byref(model.struct), _p(p), _p(da), _p(b), alc, float(scale),
-                                                   _p(T), _p(world), _stream()))
+                                                   _p(T), _p(world), ctx.stream()))
     return world[:model.n_verts], world[model.n_verts:], T
 
 

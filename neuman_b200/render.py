@@ -61,7 +61,7 @@ def render_vanilla_range(coarse_net, cap, fine_net=None, samples_per_ray=64, imp
         else:
             rgb, depth = torch.empty(n, 3, device=device), torch.empty(n, device=device)
         ctx.check(ctx.lib.nm_render_vanilla(ctx.h, cs, fs, C.byref(cam), C.byref(o), pix0, n, ops._p(rgb), ops._p(depth),
-                                            int(host_out), ops._stream()))
+                                            int(host_out), ctx.stream()))
     return rgb, depth
 
 
@@ -100,7 +100,7 @@ def render_smpl_nerf_range(net, cap, posed_verts, faces, Ts, samples_per_ray=64,
         else:
             rgb, depth, acc = torch.empty(n, 3, device=device), torch.empty(n, device=device), torch.empty(n, device=device)
         ctx.check(ctx.lib.nm_render_smpl_nerf(ctx.h, hs, 0, C.byref(cam), C.byref(o), pix0, n, ops._p(rgb), ops._p(depth),
-                                              ops._p(acc), int(host_out), ops._stream()))
+                                              ops._p(acc), int(host_out), ctx.stream()))
     return rgb, depth, acc
 
 
@@ -141,7 +141,7 @@ def _hybrid(bkg_model, human_models, cap, posed_verts, faces, Ts, S, N, white_bk
         else:
             rgb, depth, acc = torch.empty(n, 3, device=device), torch.empty(n, device=device), torch.empty(n, device=device)
         ctx.check(ctx.lib.nm_render_hybrid(ctx.h, cs, fs, na, hs, ac, int(multi), C.byref(cam), C.byref(o), pix0, n,
-                                           ops._p(rgb), ops._p(depth), ops._p(acc), int(host_out), ops._stream()))
+                                           ops._p(rgb), ops._p(depth), ops._p(acc), int(host_out), ctx.stream()))
     return rgb, depth, acc
 
 

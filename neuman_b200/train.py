@@ -71,14 +71,36 @@ def weight_reset(m):
         m.reset_parameters()
 
 
-def train_batch(coarse_net, fine_net, optimizer, batch, opt, iteration=0, **kw):
+def train_batch(coarse_net, fine_net, optimizer, batch, opt, iteration=0, nan_guard='device', **kw):
     """trainers/vanilla_nerf_trainer.py:206-223.  Returns the total loss as a 0-d tensor (no host sync
-    unless the caller reads it)."""
+    unless the caller reads it).
+
+    The reference skips the backward pass when the loss is NaN (:214-218).  Here the backward is an fp16-operand chain
+    with one power-of-two loss scale, so an overflow can also show up in the gradients only.  nan_guard:
+      'device' (default) -- no host sync: if the loss or any gradient is non-finite every gradient of the step is
+                            replaced by zero on the device before optimizer.step();
+      'host'             -- the reference's behaviour: read the loss on the host, zero_grad() and skip backward on NaN;
+      None               -- no guard."""
     optimizer.zero_grad()
     c_rgb, c_emp, f_rgb, f_emp = vanilla_loss_func(coarse_net, fine_net, batch, opt, **kw)
     total = c_rgb + f_rgb
     if iteration >= getattr(opt, 'delay_iters', 0):
         total = total + c_emp + f_emp
+    if nan_guard == 'host':
+        if not bool(torch.isfinite(total.detach())):
+            print('loss is nan during training')
+            optimizer.zero_grad()
+        else:
+            total.backward()
+        optimizer.step()
+        return total.detach()
     total.backward()
+    if nan_guard == 'device':
+        grads = [p.grad for g in optimizer.param_groups for p in g['params'] if p.grad is not None]
+        if grads:
+            ok = torch.isfinite(total.detach()) & torch.isfinite(torch.stack(torch._foreach_norm(grads))).all()
+            bad = ~ok
+            for g in grads:
+                g.masked_fill_(bad, 0.0)
     optimizer.step()
     return total.detach()
