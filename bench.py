@@ -6,16 +6,21 @@
 Workload (config.workload): render_vanilla -- background NeRF, 1280x720 = 921 600 rays, 128 coarse +
 128 importance samples (the fine net evaluates 256), seeded default-init weights, synthetic camera:
 BASELINE.json configs[1]'s frame at the sample counts its `metric` is quoted on.  One step = one frame.
-N > 1: the frame's rays are sharded across ranks (contiguous pixel ranges, no data-path collective) and
-one NCCL all_gather reassembles the frame -- total work is fixed, so scaling is "strong".
+N > 1: the frame's pixels are dealt to the ranks as interleaved 16x16 tiles (no data-path collective
+while rendering), one NCCL all_gather of equal shards + one un-permute kernel reassemble the frame -- total work is
+fixed, so scaling is "strong".
 
 `value`   : device-resident throughput (rays generated on device, outputs left in HBM).
 `e2e`     : the same metric through the public API that hands back host arrays: camera (host struct) in,
             frame copied device->host inside the timed region.
 `roofline`: the dominant kernel (k_mlp_tc, tcgen05 fp16xfp16->fp32) timed per launch with CUDA events on
             its own stream inside the timed region (nm_profile_*), algorithmic FLOPs = evals x 1 186 816.
-`cpu_baseline` / `--impl reference`: the oracle port of the reference's PyTorch path (oracle/), all host
-            threads, on a bounded ray subsample of the same frame.
+`configs` : BASELINE.json configs 2-5 at their stated sizes (device-resident, 1 warm + 2 timed frames each):
+            Mrays/s, MLP evaluations, hit rays, MLP TFLOP/s.
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference's own render_vanilla (baseline/_ref, installed by
+            tools/install_reference.py) on the host cores, on a 64x64-pixel block (4096 rays) of the same frame:
+            1 warm-up + 3 timed runs, median, thread count picked by a short sweep.  Falls back to the
+            oracle port (kind "port") only when the reference copy is absent.
 """
 import argparse
 import json
@@ -37,6 +42,7 @@ FLOP_PER_EVAL = 1186816
 EVALS_PER_RAY = S + (S + N)        # 384
 METRIC = "Mrays/sec @128+128 samples"
 WORKLOAD = "render_vanilla background NeRF 1280x720 (921600 rays), 128 coarse + 128 importance samples, random default-init weights"
+CPU_WINDOW = (608, 328)            # pixel block of the frame the CPU arm renders (64x64 = 4096 rays)
 
 
 def peaks():
@@ -82,45 +88,123 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_sample(n_rays, threads=None):
-    """CPU leg: the oracle port of render_vanilla on a ray subsample of the SAME frame."""
-    from oracle import neuman_oracle as no
-    from oracle import scenes
-    import neuman_b200 as nb
-    torch.set_num_threads(threads or os.cpu_count())
-    coarse, fine = scenes.seed_nets(nb.build_nerf, nb.default_opt(use_cuda=False), 1)
-    cp, fp = no.net_params_from_joiner(coarse), no.net_params_from_joiner(fine)
-    K, c2w = scenes.camera(H, W, seed=1)
-    idx = np.linspace(0, H * W - 1, n_rays).astype(np.int64)
-    t0 = time.perf_counter()
-    rgb, dep = no.render_vanilla(cp, fp, K, c2w, H, W, 0.0, 3.14, rays_per_batch=2048, samples_per_ray=S,
-                                 importance_samples_per_ray=N, ray_subset=idx)
-    dt = time.perf_counter() - t0
-    return dt, rgb, idx
+# -------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own functions on the host cores (test infrastructure: oracle/, baseline/_ref)
+# -------------------------------------------------------------------------------------------------------------
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+class CpuArm:
+    """render_vanilla of the frame's pixel block [x0, x0+w) x [y0, y0+h) on the CPU: the unmodified reference when its copy
+    is importable (kind "reference"), else the oracle port (kind "port")."""
+
+    def __init__(self):
+        from neuman_b200 import synthetic
+        from oracle import ref_import
+        self.synthetic = synthetic
+        self.K, self.c2w = synthetic.camera(H, W, seed=1)
+        self.kind = "port"
+        self.ref = None
+        if ref_import.available():
+            try:
+                self.ref = ref_import.load()
+                self.kind = "reference"
+            except Exception as e:                                   # pragma: no cover
+                print(f"bench.py: reference import failed ({e}); timing the oracle port", file=sys.stderr)
+        if self.ref is not None:
+            from oracle import ref_opts
+            self.coarse, self.fine = synthetic.seed_nets(self.ref.vanilla.build_nerf, ref_opts.default_opt(), 1)
+        else:
+            import neuman_b200 as nb
+            from oracle import neuman_oracle as no
+            coarse, fine = synthetic.seed_nets(nb.build_nerf, nb.default_opt(use_cuda=False), 1)
+            self.cp, self.fp = no.net_params_from_joiner(coarse), no.net_params_from_joiner(fine)
+
+    def render(self, x0, y0, w, h):
+        """-> (seconds, rgb [h*w,3], depth [h*w])"""
+        Kw = self.synthetic.window_camera(self.K, x0, y0)
+        torch.set_grad_enabled(False)
+        t0 = time.perf_counter()
+        if self.ref is not None:
+            import contextlib
+            import io
+            ref = self.ref
+            cam = ref.pinhole_camera.PinholeCamera(w, h, Kw[0, 0], Kw[1, 1], Kw[0, 2], Kw[1, 2])
+            pose = ref.camera_pose.CameraPose.from_camera_to_world(self.c2w.astype(np.float64))
+            cap = ref.captures.BasePinholeCapture(cam, pose)
+            cap.near, cap.far = {"bkg": 0.0}, {"bkg": 3.14}
+            with contextlib.redirect_stdout(io.StringIO()):
+                rgb, dep = ref.render_utils.render_vanilla(self.coarse, cap, fine_net=self.fine, rays_per_batch=2048,
+                                                           samples_per_ray=S, importance_samples_per_ray=N, return_depth=True)
+            rgb, dep = rgb.reshape(-1, 3), dep.reshape(-1)
+        else:
+            from oracle import neuman_oracle as no
+            rgb, dep = no.render_vanilla(self.cp, self.fp, Kw, self.c2w, h, w, 0.0, 3.14, rays_per_batch=2048,
+                                         samples_per_ray=S, importance_samples_per_ray=N)
+        return time.perf_counter() - t0, rgb, dep
+
+    def pick_threads(self):
+        """Short sweep on a 16x16 block: the thread count with the best throughput (oversubscribing both sockets' SMT
+        siblings with 2048-ray batches is several times slower than one socket's cores)."""
+        n = os.cpu_count() or 1
+        cands = sorted({c for c in (8, 16, 32, 64, n // 2, n) if 1 <= c <= n})
+        best, best_t = cands[0], None
+        sweep = {}
+        for c in cands:
+            torch.set_num_threads(c)
+            self.render(CPU_WINDOW[0], CPU_WINDOW[1], 16, 16)        # warm
+            dt, _, _ = self.render(CPU_WINDOW[0], CPU_WINDOW[1], 16, 16)
+            sweep[c] = round(dt, 3)
+            if best_t is None or dt < best_t:
+                best, best_t = c, dt
+        torch.set_num_threads(best)
+        return best, sweep
+
+    def measure(self, runs=3, warm=1, side=64, budget_s=150.0):
+        threads, sweep = self.pick_threads()
+        x0, y0 = CPU_WINDOW
+        dt, rgb, dep = self.render(x0, y0, side, side)               # warm-up (also sizes the sample)
+        while side > 16 and dt * (runs + warm) > budget_s:
+            side //= 2
+            dt, rgb, dep = self.render(x0, y0, side, side)
+        times = []
+        for _ in range(runs):
+            dt, rgb, dep = self.render(x0, y0, side, side)
+            times.append(dt)
+        med = float(np.median(times))
+        n_rays = side * side
+        return {"value": n_rays / med / 1e6, "unit": "Mrays/s", "cores": threads, "kind": self.kind,
+                "sample": (f"{side}x{side} pixel block at ({x0},{y0}) of the same 1280x720 frame = {n_rays} rays, 128+128, "
+                           f"{'unmodified reference render_vanilla (baseline/_ref)' if self.kind == 'reference' else 'torch-CPU oracle port'}, "
+                           f"1 warm-up + {runs} runs, median {med:.2f} s; {threads} threads of {os.cpu_count()} logical CPUs "
+                           f"({cpu_model()}), 16x16-block thread sweep s: {sweep}"),
+                "cpu_model": cpu_model(), "times_s": [round(t, 3) for t in times]}, (x0, y0, side), rgb, dep
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    n_rays = 1024
-    cores = os.cpu_count()
-    times = []
-    for i in range(args.warmup + args.steps):
-        dt, _, _ = oracle_sample(n_rays)
-        if i >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * float(np.mean(times))
-    val = n_rays / (ms * 1e3)
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+    arm = CpuArm()
+    runs = max(1, min(args.steps, 5))
+    cb, _, _, _ = arm.measure(runs=runs, warm=max(1, min(args.warmup, 2)))
+    ms = 1e3 * float(np.median(cb["times_s"]))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": runs,
+            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"{n_rays} rays of the frame per step (bounded CPU sample)"},
-            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                             "sample": f"{n_rays}-ray subsample of the 1280x720 frame, 128+128, torch-CPU oracle port of the reference path, {cores} threads"},
-            "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "config": {"workload": WORKLOAD, "sample": cb["sample"], "timing": "median of the timed steps (BASELINE.md §3)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+# -------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -128,6 +212,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg2-5 side measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -153,8 +238,8 @@ def main():
     K, c2w = scenes.camera(H, W, seed=1)
     cap = nb.SimpleCapture(K, c2w, H, W, 0.0, 3.14)
     n_pix = H * W
-    p0, cnt = sharding.shard_range(n_pix, rank, world)
     ctx = Context.get(local)
+    part = sharding.TilePartition(H, W, rank, world, device=dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -163,9 +248,9 @@ def main():
         torch.cuda.synchronize()
 
     def step_device():
-        rgb, depth = render.render_vanilla_range(coarse, cap, fine, S, N, pix0=p0, n=cnt, host_out=False)
-        frame = sharding.gather_frame(torch.cat([rgb, depth[:, None]], 1), n_pix, rank, world)
-        return frame
+        rgb, depth, _ = part.buffers(with_acc=False)
+        render.render_vanilla_range(coarse, cap, fine, S, N, pixels=part.pixels, host_out=False, out=(rgb, depth))
+        return part.gather()                        # (rgb [H*W,3], depth [H*W], None) on every rank
 
     def step_e2e():
         if world == 1:
@@ -173,8 +258,8 @@ def main():
             rgb, depth = nb.render_vanilla(coarse, cap, fine_net=fine, samples_per_ray=S, importance_samples_per_ray=N,
                                            return_depth=True)
             return rgb
-        frame = step_device()
-        host = frame.cpu() if rank == 0 else None
+        rgb, depth, _ = step_device()
+        host = (rgb.cpu(), depth.cpu()) if rank == 0 else None
         return host
 
     def timed(fn, steps):
@@ -193,13 +278,12 @@ def main():
     # warm-up: at least W (>= 3) frames, and -- the board runs into its power cap within a few seconds of this
     # workload -- at least 3 s, so that the device-resident and the end-to-end measurements below see the same
     # steady-state clocks (bounded to 12 frames)
-    import time as _time
-    t_w, n_w, go = _time.time(), 0, True
+    t_w, n_w, go = time.time(), 0, True
     while go:
         step_device()
         torch.cuda.synchronize()
         n_w += 1
-        go = n_w < max(args.warmup, 3) or (_time.time() - t_w < 3.0 and n_w < 12 * world)
+        go = n_w < max(args.warmup, 3) or (time.time() - t_w < 3.0 and n_w < 12 * world)
         if world > 1:                                   # every rank must run the same number of frames (collective inside)
             flag = torch.tensor([1 if go else 0], device=dev)
             dist.broadcast(flag, 0)
@@ -220,9 +304,14 @@ def main():
         step_e2e()
     ms_e2e, host = timed(step_e2e, args.steps)
     e2e_val = n_pix / (ms_e2e / args.steps * 1e3)
+    ctx.range_check()                                   # raises if any launch saturated an fp16 operand
+
+    pk = peaks()
+    side = {}
+    if not args.no_configs:
+        side = side_configs(nb, render, sharding, scenes, ctx, dev, rank, world, dist, pk)
 
     if rank == 0:
-        pk = peaks()
         mlp_ms_per_launch = prof["mlp_ms"] / max(prof["mlp_launches"], 1)
         flops_per_launch = prof["mlp_evals"] / max(prof["mlp_launches"], 1) * FLOP_PER_EVAL
         achieved = flops_per_launch / (mlp_ms_per_launch * 1e-3) / 1e12 if prof["mlp_ms"] > 0 else None
@@ -231,34 +320,136 @@ def main():
         tp = os.path.join(ROOT, "profiles", "mlp_tc_traffic.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
-            # DRAM bytes of one ncu-captured launch, scaled to this run's evaluations per launch
-            traffic = tj["dram_bytes_per_launch"] / tj["evals_per_launch"] * (prof["mlp_evals"] / max(prof["mlp_launches"], 1))
+            traffic = tj.get("dram_bytes_per_launch_bench")       # ncu capture of THIS workload's launches (mean of S=128 and S=256)
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16 operands x f32 accumulate (tcgen05 kind::f16); f32 elsewhere", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_rays_per_step": n_pix, "mlp_evals_per_ray": EVALS_PER_RAY,
-                       "parallelism": f"ray-shard x{world} + 1 all_gather", "warmup_frames_run": n_w, "l2": "per-step working set (raw [32768x256x4] f32 chunks, 3.8 GB/frame) >> 126 MB L2; no flush needed"},
+                       "parallelism": f"ray-shard x{world}: interleaved 16x16 pixel tiles + 1 all_gather + un-permute kernel", "warmup_frames_run": n_w,
+                       "l2": "per-step working set (raw [32768x256x4] f32 chunks, 3.8 GB/frame) >> 126 MB L2; no flush needed"},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write of one captured launch, scaled per evaluation; algorithmic 20 B/eval mostly stays in L2)",
+                         "traffic": traffic, "traffic_unit": "DRAM bytes per launch: ncu dram__bytes_read+write of this workload's two launch shapes (32768 rays x 128 / x 256 samples), mean; algorithmic 20 B/eval mostly stays in L2",
                          "kernel": "k_mlp_tc<2>", "peak_source": pk["source"] + " bf16_tflops_sustained (fp16 runs at the bf16 rate)",
                          "mlp_launches": prof["mlp_launches"], "mlp_ms_per_step": prof["mlp_ms"] / args.steps,
                          "mlp_share_of_step": prof["mlp_ms"] / ms_total},
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": 208, "d2h_bytes_per_step": n_pix * 4 * 4,
                     "api": "neuman_b200.render_vanilla(coarse, cap, fine_net=fine, ...) -> numpy rgb [720,1280,3] + depth (reference signature); "
                            "inputs = the capture's K / camera_to_world (208 B host struct), rays are generated on the device"},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "configs": side,
         }
         if not args.no_cpu_baseline and world == 1:
-            n_cpu = 1024
-            dt, rgb_cpu, idx = oracle_sample(n_cpu)
-            line["cpu_baseline"] = {"value": n_cpu / dt / 1e6, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"{n_cpu}-ray subsample of the same frame, 128+128, torch-CPU oracle port, {dt:.1f} s"}
-            got = frame[idx, :3].cpu().numpy()
-            line["parity_vs_cpu_sample"] = {"max_abs_rgb": float(np.abs(got - rgb_cpu).max())}
+            arm = CpuArm()
+            cb, (x0, y0, sd), rgb_cpu, dep_cpu = arm.measure()
+            line["cpu_baseline"] = cb
+            fr = frame[0].reshape(H, W, 3)[y0:y0 + sd, x0:x0 + sd].reshape(-1, 3).cpu().numpy()
+            fd = frame[1].reshape(H, W)[y0:y0 + sd, x0:x0 + sd].reshape(-1).cpu().numpy()
+            line["parity_vs_cpu_sample"] = {"rays": int(sd * sd), "max_abs_rgb": float(np.abs(fr - rgb_cpu).max()),
+                                            "max_abs_depth": float(np.abs(fd - dep_cpu).max()),
+                                            "note": "depth gate = max(1e-4, 1.5 x the 11-bit-operand floor of the oracle on the same rays), tests/test_gpu_fullsize.py"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def side_configs(nb, render, sharding, scenes, ctx, dev, rank, world, dist, pk):
+    """BASELINE.json configs 2-5 at their stated sizes, device-resident, sharded like the main workload.  Bodies come from
+    the device SMPL kernels (ops.smpl_scene_transforms) on the synthetic SMPL-shaped model."""
+    from neuman_b200 import ops
+    torch.manual_seed(1)
+    model = nb.HumanNeRF(nb.default_opt(use_cuda=False))
+    scenes.boost_density(model.coarse_human_net)
+    model = model.to(dev)
+    sm = scenes.make_model(0)
+    par = sm["kintree_table"][0].astype(np.int64)
+    smpl = ops.SmplModelDevice(sm["v_template"], sm["shapedirs"], sm["J_regressor"], sm["weights"], par, device=dev)
+    faces = torch.from_numpy(sm["f"].astype(np.int32)).to(dev)
+    out = {}
+
+    def bodies_of(cfg):
+        bs = []
+        for a in cfg["actors"]:
+            pose, betas, align = scenes.actor_pose(a)
+            verts, joints, T = ops.smpl_scene_transforms(smpl, pose, betas, align, a["scale"])
+            bs.append({"verts": verts.contiguous(), "T": T, "geo": float(torch.linalg.norm(joints[3] - joints[0]))})
+        return bs
+
+    for name in ("cfg2", "cfg3_can", "cfg3", "cfg4", "cfg5"):
+        cfg = scenes.FULLSIZE[name.split("_")[0]]
+        Hc, Wc, Sc, Nc = cfg["H"], cfg["W"], cfg["S"], cfg["N"]
+        K, c2w = scenes.fullsize_camera(name.split("_")[0])
+        cap = nb.SimpleCapture(K, c2w, Hc, Wc, cfg["near"], cfg["far"])
+        part = sharding.TilePartition(Hc, Wc, rank, world, device=dev)
+        bs = bodies_of(cfg)
+        geo = bs[0]["geo"] if bs else 0.2
+        if name == "cfg2":
+            cn, fn_ = model.coarse_bkg_net, model.fine_bkg_net
+
+            def fn():
+                rgb, depth, _ = part.buffers(with_acc=False)
+                render.render_vanilla_range(cn, cap, fn_, Sc, Nc, pixels=part.pixels, host_out=False, out=(rgb, depth))
+                return part.gather()
+        elif name.startswith("cfg3"):
+            can = name.endswith("_can")
+
+            def fn():
+                bufs = part.buffers()
+                render.render_smpl_nerf_range(model, cap, bs[0]["verts"], faces, bs[0]["T"], Sc, True, can, geo, 1.0,
+                                              pixels=part.pixels, host_out=False, out=bufs)
+                return part.gather()
+        elif name == "cfg4":
+            def fn():
+                bufs = part.buffers()
+                render.render_hybrid_nerf_range(model, cap, bs[0]["verts"], faces, bs[0]["T"], Sc, Nc, True, geo,
+                                                pixels=part.pixels, host_out=False, out=bufs)
+                return part.gather()
+        else:
+            def fn():
+                bufs = part.buffers()
+                render._hybrid(model, [model] * len(bs), cap, [b["verts"] for b in bs], [faces] * len(bs), [b["T"] for b in bs],
+                               Sc, Nc, True, geo, True, 0, None, False, render.CHUNK, pixels=part.pixels, out=bufs)
+                return part.gather()
+        fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ctx.profile(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = 2
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        prof = ctx.profile_read()
+        ctx.profile(False)
+        st = ctx.render_stats()
+        t = torch.tensor([e0.elapsed_time(e1) / reps, prof["mlp_ms"] / reps, float(st["mlp_evals"]), float(st["hit_rays"])],
+                         device=dev, dtype=torch.float64)
+        if world > 1:
+            tmax, tsum = t.clone(), t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            ms, mlp_ms, evals, hits = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tsum[3])
+            busy = [float(x) for x in _gather_scalars(dist, t[0], world, dev)]
+            hit_per_rank = [int(x) for x in _gather_scalars(dist, t[3], world, dev)]
+        else:
+            ms, mlp_ms, evals, hits = (float(x) for x in t)
+            busy, hit_per_rank = [ms], [int(hits)]
+        tf = evals / world * FLOP_PER_EVAL / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else None
+        out[name] = {"driver": cfg["driver"] + (" render_can=True" if name.endswith("_can") else ""), "frame": f"{Wc}x{Hc}",
+                     "samples": f"{Sc}+{Nc}", "ms_per_frame": ms, "Mrays_s": Hc * Wc / ms / 1e3, "mlp_evals": int(evals),
+                     "hit_rays": int(hits), "mlp_ms": mlp_ms, "mlp_tflops_per_gpu": tf,
+                     "mlp_frac_of_peak": tf / pk["tflops_sustained"] if tf else None,
+                     "non_mlp_share": 1.0 - mlp_ms / ms if ms > 0 else None,
+                     "per_rank_ms": busy, "per_rank_hit_rays": hit_per_rank}
+    return out
+
+
+def _gather_scalars(dist, x, world, dev):
+    buf = torch.zeros(world, device=dev, dtype=torch.float64)
+    dist.all_gather_into_tensor(buf, x.reshape(1).to(torch.float64))
+    return buf.tolist()
 
 
 if __name__ == "__main__":

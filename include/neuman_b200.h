@@ -33,7 +33,8 @@ typedef enum {
   NM_ERR_INVALID = -1,     /* bad argument                              */
   NM_ERR_CUDA = -2,        /* CUDA runtime error (see nm_last_error)    */
   NM_ERR_UNSUPPORTED = -3, /* shape / option outside what is built      */
-  NM_ERR_STATE = -4        /* slot not packed, mesh not set, ...        */
+  NM_ERR_STATE = -4,       /* slot not packed, mesh not set, ...        */
+  NM_ERR_RANGE = -5        /* fp16 operand range exceeded (nm_range_status) */
 } nm_status;
 
 /* positional encoding kinds: models/vanilla.py:60-79 ('posenc'), :44-58 ('rotate') */
@@ -252,25 +253,42 @@ typedef struct {
   float interval_comp;
 } nm_render_opts;
 
-/* All drivers render the row-major pixel range [pix0, pix0+n) (ray sharding across GPUs) into
- * caller buffers rgb [n,3], depth [n], acc [n] (acc may be NULL).  `host_out` != 0: the output
- * pointers are HOST memory and the call copies device->host and synchronises before returning. */
+/* All drivers render n pixels of the frame into caller buffers rgb [n,3], depth [n], acc [n] (acc may be NULL):
+ * the row-major pixel range [pix0, pix0+n) when `pixels` is NULL, else the row-major pixel indices pixels[0..n)
+ * (DEVICE int32; pix0 ignored) -- the ray shard of one GPU, e.g. its interleaved 16x16 tiles.
+ * `host_out` != 0: the output pointers are HOST memory and the call copies device->host and synchronises before
+ * returning. */
 int nm_render_vanilla(nm_ctx* ctx, int coarse_slot, int fine_slot /* -1 = none */,
                       const nm_camera* cam, const nm_render_opts* opt, int64_t pix0, int64_t n,
-                      float* rgb, float* depth, int32_t host_out, void* stream);
+                      const int32_t* pixels, float* rgb, float* depth, int32_t host_out, void* stream);
 int nm_render_smpl_nerf(nm_ctx* ctx, int human_slot, int actor, const nm_camera* cam,
-                        const nm_render_opts* opt, int64_t pix0, int64_t n, float* rgb,
+                        const nm_render_opts* opt, int64_t pix0, int64_t n, const int32_t* pixels, float* rgb,
                         float* depth, float* acc, int32_t host_out, void* stream);
 int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int32_t n_actors,
                      const int32_t* human_slots, const int32_t* actors, int32_t multi_person,
                      const nm_camera* cam, const nm_render_opts* opt, int64_t pix0, int64_t n,
-                     float* rgb, float* depth, float* acc, int32_t host_out, void* stream);
+                     const int32_t* pixels, float* rgb, float* depth, float* acc, int32_t host_out, void* stream);
+
+/* Reassembly of a frame from the ranks' shards after the one gather of SURVEY.md §8e (the reference concatenates its
+ * batches and reshapes, utils/render_utils.py:157-161; here a shard is a pixel list).  `shards` is the gathered buffer
+ * [world][planes * per] floats, each shard laid out as rgb [per,3] | depth [per] | acc [per] (planes = 5) or without acc
+ * (planes = 4); pixels_all [world * per] DEVICE int32 holds the row-major pixel index of every shard entry, < 0 for the
+ * padding of short shards.  Writes rgb [HW,3], depth [HW] and acc [HW] (acc may be NULL). */
+int nm_assemble_frame(nm_ctx* ctx, const float* shards, int32_t world, int64_t per, int32_t planes,
+                      const int32_t* pixels_all, float* rgb, float* depth, float* acc, void* stream);
 
 /* Optional timing of the MLP kernel launches (the dominant kernel; bench.py's roofline): when enabled,
  * every MLP launch is bracketed by CUDA events on its own stream.  nm_profile_read synchronises on
  * them and returns the summed device time, the number of launches and of network evaluations. */
 int nm_profile_enable(nm_ctx* ctx, int32_t on);
 int nm_profile_read(nm_ctx* ctx, double* mlp_ms, int64_t* mlp_launches, int64_t* mlp_evals);
+
+/* Range guard of the tensor-core MLP (NM_MLP_TC_F16).  Its operands are fp16: conversions saturate at +-65504
+ * (cvt.satfinite) instead of producing inf, and every kernel ORs a sticky flag into device memory when an encoded input
+ * or a hidden activation reached that limit.  The reference has no counterpart (its fp32 nets cannot overflow at such
+ * magnitudes, models/vanilla.py:120-152); this is the check a trained checkpoint with large activations needs.
+ * Synchronises on `stream`, returns NM_ERR_RANGE if the flag was set since the last clearing call, NM_OK otherwise. */
+int nm_range_status(nm_ctx* ctx, int32_t clear, void* stream);
 
 /* statistics of the last driver call on this ctx: number of MLP evaluations executed (for the
  * roofline: x 1,186,816 FLOP) and number of hit rays. */

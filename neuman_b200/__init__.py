@@ -6,7 +6,8 @@ reference's own function / module signatures.  See DESIGN.md and INTEGRATION.md.
     nb.install()     # rebind the reference's utils.render_utils / utils.ray_utils / models.vanilla
 """
 from . import _lib
-from .models import Embedder, NeRF, Joiner, HumanNeRF, build_nerf, default_opt     # noqa: F401
+from .models import (Embedder, NeRF, Joiner, OffsetNet, HumanNeRF, SMPL, build_nerf, build_offset_net,      # noqa: F401
+                     default_opt)
 from .ops import (raw2outputs, ray_to_samples, ray_to_importance_samples, sample_pdf,          # noqa: F401
                   geometry_guided_near_far, warp_samples_to_canonical, warp_samples_to_canonical_diff, signed_distance,
                   shot_rays, shot_all_rays,

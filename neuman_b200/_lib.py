@@ -76,15 +76,17 @@ SIGNATURES = {
     "nm_smpl_vertex_transforms": (C.c_int, [_P, C.POINTER(NmSmplModel), _P, _P, _I32, _P, _P, _P]),
     "nm_smpl_scene_transforms": (C.c_int, [_P, C.POINTER(NmSmplModel), _P, _P, _P, C.POINTER(C.c_double), C.c_double,
                                            _P, _P, _P]),
-    "nm_render_vanilla": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(NmCamera), C.POINTER(NmRenderOpts), _I64, _I64,
+    "nm_render_vanilla": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(NmCamera), C.POINTER(NmRenderOpts), _I64, _I64, _P,
                                     _P, _P, _I32, _P]),
-    "nm_render_smpl_nerf": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(NmCamera), C.POINTER(NmRenderOpts), _I64, _I64,
+    "nm_render_smpl_nerf": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(NmCamera), C.POINTER(NmRenderOpts), _I64, _I64, _P,
                                       _P, _P, _P, _I32, _P]),
     "nm_render_hybrid": (C.c_int, [_P, C.c_int, C.c_int, _I32, C.POINTER(_I32), C.POINTER(_I32), _I32,
-                                   C.POINTER(NmCamera), C.POINTER(NmRenderOpts), _I64, _I64, _P, _P, _P, _I32, _P]),
+                                   C.POINTER(NmCamera), C.POINTER(NmRenderOpts), _I64, _I64, _P, _P, _P, _P, _I32, _P]),
+    "nm_assemble_frame": (C.c_int, [_P, _P, _I32, _I64, _I32, _P, _P, _P, _P, _P]),
     "nm_profile_enable": (C.c_int, [_P, _I32]),
     "nm_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(_I64), C.POINTER(_I64)]),
     "nm_last_render_stats": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),
+    "nm_range_status": (C.c_int, [_P, _I32, _P]),
 }
 
 _lib = None
@@ -147,6 +149,11 @@ class Context:
     def check(self, rc):
         if rc != 0:
             raise NmError(f"libneuman_b200 error {rc}: {self.lib.nm_last_error(self.h).decode()}")
+
+    def range_check(self, clear=True):
+        """Raises NmError (NM_ERR_RANGE) if a tensor-core MLP launch saturated an fp16 operand since the last check.
+        Synchronises on the current stream."""
+        self.check(self.lib.nm_range_status(self.h, int(bool(clear)), self.stream()))
 
     def launch_count(self):
         return int(self.lib.nm_launch_count(self.h))

@@ -21,6 +21,7 @@ extern "C" int nm_ctx_create(int device, nm_ctx** out) {
     delete c;
     return NM_ERR_CUDA;
   }
+  cudaMemset(c->d_counter, 0, 64 * sizeof(int32_t));
   *out = c;
   return NM_OK;
 }
@@ -29,6 +30,7 @@ static void free_net(NmNet& n) {
   if (n.f32) cudaFree(n.f32);
   if (n.f16) cudaFree(n.f16);
   if (n.tc_bias) cudaFree(n.tc_bias);
+  if (n.consts_host) cudaFreeHost(n.consts_host);
   if (n.f16_bwd) cudaFree(n.f16_bwd);
   if (n.bw_wrgb) cudaFree(n.bw_wrgb);
   n = NmNet();
@@ -44,6 +46,8 @@ static void free_mesh(NmMesh& m) {
   if (m.vnorm) cudaFree(m.vnorm);
   if (m.adj) cudaFree(m.adj);
   if (m.pn_tmp) cudaFree(m.pn_tmp);
+  if (m.vsorted) cudaFree(m.vsorted);
+  if (m.vgroup) cudaFree(m.vgroup);
   m = NmMesh();
 }
 
@@ -85,6 +89,20 @@ extern "C" int nm_profile_read(nm_ctx* ctx, double* mlp_ms, int64_t* mlp_launche
   if (mlp_ms) *mlp_ms = total;
   if (mlp_launches) *mlp_launches = (int64_t)(ctx->prof_used / 2);
   if (mlp_evals) *mlp_evals = ctx->prof_evals;
+  return NM_OK;
+}
+
+extern "C" int nm_range_status(nm_ctx* ctx, int32_t clear, void* stream) {
+  NM_ENTER(ctx);
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* d = ctx->d_counter + NM_RANGE_FLAG_WORD;
+  int32_t* h = ctx->h_counter + NM_RANGE_FLAG_WORD;
+  NM_CHECK_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (clear) NM_CHECK_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(int32_t), st));
+  NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+  if (*h != 0)
+    NM_FAIL(ctx, NM_ERR_RANGE, "tensor-core MLP: an input or hidden activation reached the fp16 range limit (|x| >= 65504) and was "
+                               "saturated; results of the affected samples are not reliable (use NM_MLP_SIMT_F32 for such networks)");
   return NM_OK;
 }
 
@@ -267,7 +285,7 @@ static int mlp_dispatch(nm_ctx* ctx, int slot, int mode, const float* pts, const
     NM_FAIL(ctx, NM_ERR_STATE, "nm_mlp_forward: net slot not packed");
   if (n < 0 || !raw) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward: bad argument");
   if (n == 0) return NM_OK;
-  const NmNet& net = ctx->nets[slot];
+  NmNet& net = ctx->nets[slot];
   if (mode != NM_MLP_SIMT_F32 && mode != NM_MLP_TC_F16) NM_FAIL(ctx, NM_ERR_INVALID, "nm_mlp_forward: unknown mode");
   cudaStream_t st = (cudaStream_t)stream;
   cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -32,12 +32,20 @@
 // Plan: which slabs a step consumes, where they live in the packed image.
 // ---------------------------------------------------------------------------------------------
 struct TcPlan {
-  uint32_t slab_off[TC_STEPS][5];   // byte offset inside one CTA-rank image
-  uint32_t slab_bytes[TC_STEPS];    // bytes per slab of this step (per CTA)
+  uint32_t slab_off[TC_STEPS][6];   // byte offset inside one CTA-rank image
+  uint32_t slab_bytes[TC_STEPS];    // bytes per weight slab of this step (per CTA); its bias slab is a quarter of that
   uint32_t image_bytes;             // size of one CTA-rank image
 };
 
-__host__ __device__ constexpr int step_nkb(int s) { return s == 0 ? 1 : (s == 5 || s == 9) ? 5 : (s == 10 ? 2 : 4); }
+// Every layer's bias rides in the MMAs: each step 0..9 ends with one extra k-block, a "bias slab" [N rows][K = 16]
+// whose first two K columns hold the bias split into two fp16 values (hi + lo: 22 significand bits, fp32 accuracy after
+// the fp32 accumulation), multiplied by a constant A operand whose rows are all (1, 1, 0, ..., 0).  That operand is 256
+// bytes of shared memory: a K-major SWIZZLE_NONE descriptor with a zero stride between the 8-row groups makes all 128
+// rows read the same two core matrices.  The epilogue then has no bias loads and no adds at all -- they were its largest
+// cost (4 LDS.128 broadcasts + 16 FADD per 16 columns on the pipe that also feeds the UMMA operands and takes the
+// activation stores: profiles/r02_mlp_tc_experiments.md); one K = 16 MMA per step costs 1/16 of a layer's tensor time.
+__host__ __device__ constexpr int step_nkb(int s) { return s == 0 ? 2 : (s == 5 || s == 9) ? 6 : (s == 10 ? 2 : 5); }
+__host__ __device__ constexpr bool kb_is_bias(int s, int kb) { return s <= 9 && kb == step_nkb(s) - 1; }
 __host__ __device__ constexpr int step_N(int s) { return s <= 8 ? 256 : (s == 9 ? 128 : 16); }
 // k-block kb of step s reads the PE buffer (else activation block `act_kb`)
 __host__ __device__ constexpr bool kb_is_pe(int s, int kb) { return (s == 0) || (s == 5 && kb == 0) || (s == 9 && kb == 4); }
@@ -49,30 +57,43 @@ struct TcCfg {
   static constexpr int NT = kPair == 2 ? 2 : 1;
   static constexpr int NSLOT = kPair == 2 ? 5 : 4;
   static constexpr int SLOT_BYTES = 32768 / kPair;
-  static constexpr int THREADS = 64 + 256;        // producer + MMA warps, 8 epilogue warps
+  static constexpr int THREADS = 64 + 256 + 128;  // producer + MMA warps, 8 epilogue warps, 4 encoding warps
   static constexpr int OFF_ACT = 0;
   static constexpr int OFF_PE = OFF_ACT + NT * 4 * TC_KB_BYTES;
   static constexpr int OFF_RING = OFF_PE + TC_KB_BYTES;
   static constexpr int OFF_BAR = OFF_RING + NSLOT * SLOT_BYTES;
-  // barriers: full[NSLOT] peer_full[NSLOT] empty[NSLOT] tmem_full[NT] act_ready[NT] pe_free
-  static constexpr int N_BAR = 3 * NSLOT + 2 * NT + 1;
+  // barriers: full[NSLOT] peer_full[NSLOT] empty[NSLOT] tmem_full[NT] act_ready[NT] pe_free pe_ready
+  static constexpr int N_BAR = 3 * NSLOT + 2 * NT + 2;
   static constexpr int OFF_TMEMPTR = OFF_BAR + 8 * N_BAR;
-  // per-warpgroup copy of the current step's bias row (256 fp32), refreshed each step by the warpgroup
-  static constexpr int OFF_BIAS = (OFF_TMEMPTR + 16 + 127) & ~127;
-  static constexpr int SMEM_USED = OFF_BIAS + 1024 + NT * 512;   // bias row + alpha partials
+  // alpha-head partials of the upper column half, one float per row and tile in flight
+  static constexpr int OFF_ALPHA = (OFF_TMEMPTR + 16 + 127) & ~127;
+  // constant A operand of the bias MMAs: two 8 x 16 B core matrices, every row = (1, 1, 0, 0, 0, 0, 0, 0 | 0 x 8) in fp16
+  static constexpr int OFF_ONES = OFF_ALPHA + NT * 512;
+  static constexpr int SMEM_USED = OFF_ONES + 256;
   static constexpr int SMEM_SLACK = (232448 - SMEM_USED) < 1024 ? (232448 - SMEM_USED) : 1024;   // alignment slack that still fits 227 KB
   static constexpr int SMEM_BYTES = SMEM_USED + SMEM_SLACK;
 };
 
+// What the epilogue threads still multiply or add with, the same for every row -- the alpha_linear weights (the alpha
+// head runs in fp32 on the unrounded post-ReLU layer-7 accumulators, models/vanilla.py:135) and the four output biases --
+// is read from a CONSTANT BANK through the uniform datapath (LDCU.128 into uniform registers, then `FFMA R, R, UR, R`): no
+// shared-memory loads (the LSU / shared-memory pipe is the busiest unit of this kernel: UMMA operand fetches + activation
+// stores) and no vector registers.  Inference launches carry the table as kernel parameters (bank 0); the training forward, whose weights are
+// re-packed on the device every optimiser step, reads a __constant__ copy refreshed by a stream-ordered
+// device-to-device copy in front of the launch (filling kernel parameters would need a host round trip per step).
+//   [0, 256) alpha_linear.weight | 256..258 rgb bias | 259 alpha bias
+#define TC_CONST_ALPHA 0
+#define TC_CONST_OUT 256
+__constant__ __align__(16) float c_tc_consts[TC_CONST_FLOATS];
+
 struct TcParams {
   const uint8_t* wimg;      // packed slabs, kPair images back to back
-  const float* bias;        // [12][256]: rows 0-9 the steps' biases, row 10 = {rgb_b0,rgb_b1,rgb_b2,alpha_b}, row 11 = alpha weights
   TcPlan plan;
   NmMlpInput in;
   NmPeSpec pos_pe, dir_pe;
   float* raw;
   long long n_tiles;        // number of (pair-)tiles
-  int cslot;                // index of this net's bias table in c_tc_bias (kConst kernels)
+  int32_t* range_flag;      // device word: bit 0 is set when an activation reached the fp16 range limit (saturated)
   // training forward (kTrain): fp16 activation stash for the backward pass, planes of n rows each
   __half* st_x;             // [8][n][256] post-ReLU outputs of layers 0..7
   __half* st_f;             // [n][256]    feature_linear output
@@ -82,7 +103,15 @@ struct TcParams {
   CUtensorMap map_x, map_f, map_v;   // TMA store maps of st_x / st_f / st_v (kTrain only)
   int dbg;                  // debug (NEUMAN_TC_DEBUG): bit 0 = training kernel skips its TMA stash stores (timing experiments only)
   long long* trace;         // optional debug timeline (tools/tc_trace.py): [cta<2][role<2][event<4][256] clock64 stamps
+  __align__(16) float consts[TC_CONST_FLOATS];   // inference: the constant table as kernel parameters
 };
+
+template <bool kParam>
+__device__ __forceinline__ float4 cst4(const TcParams& P, int i) {      // i % 4 == 0
+  return kParam ? *reinterpret_cast<const float4*>(&P.consts[i]) : *reinterpret_cast<const float4*>(&c_tc_consts[i]);
+}
+template <bool kParam>
+__device__ __forceinline__ float cst(const TcParams& P, int i) { return kParam ? P.consts[i] : c_tc_consts[i]; }
 
 // sin/cos of 2*pi*f (f in cycles).  The operands of the tensor-core path are fp16 (quantisation 2.4e-4 on a
 // [-1,1] value), so the encodings only need ~1e-5: range reduction is done exactly in "cycles" with a
@@ -153,65 +182,54 @@ __device__ __forceinline__ void store_row_swizzled(uint8_t* blk, int row, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Epilogue of one 32-column chunk: +bias (from the warpgroup's shared-memory copy of the step's bias
-// row: every lane reads the same address, a broadcast), the alpha head on step 7 (alpha weights are
-// spread over the lanes' registers, 8 per lane, and fetched by shuffle), ReLU, f16x2 pack, swizzled
-// 16-byte stores into the activation block that is the next step's A operand.
+// Epilogue of 16 accumulator columns [c0, c0+16) of one row: + bias, the alpha head on step 7 (fp32 FFMAs on the
+// ReLU of the unrounded accumulators), ReLU, saturating f16x2 pack, two swizzled 16-byte stores into the activation
+// block that is the next step's A operand.  c0 is a compile-time constant and `crow` (= step * 256) warp-uniform, so
+// the bias and the alpha weights are uniform-register operands.
 // ---------------------------------------------------------------------------------------------
-#define TC_BIAS_ROWS 12
-#define TC_BIAS_FLOATS (TC_BIAS_ROWS * TC_BIAS_STRIDE)
-
 template <bool RELU>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   uint32_t d;
-  if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  if (RELU) asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
 
-// Up to TC_CONST_NETS nets keep their bias table in __constant__ memory: every lane reads the same address, so
-// the constant cache broadcasts it and the loads stay off the shared-memory crossbar (which the UMMA operand
-// fetches and the activation stores already load to >80 %).  Further nets use a bias row staged in smem.
-#define TC_CONST_NETS 5
-__constant__ float c_tc_bias[TC_CONST_NETS * TC_BIAS_FLOATS];
-
-template <bool kConst>
-__device__ __forceinline__ void load_bias16(float4 (&b)[4], const float* sbias, int cidx) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (kConst) b[g] = *reinterpret_cast<const float4*>(&c_tc_bias[cidx + 4 * g]);
-    else b[g] = *reinterpret_cast<const float4*>(sbias + 4 * g);
-  }
+// running maximum of |activation| as packed halves (range flag)
+template <bool RELU>
+__device__ __forceinline__ void track_range(uint32_t& rng, uint32_t packed) {
+  __half2 h = *reinterpret_cast<const __half2*>(&packed);
+  if (!RELU) h = __habs2(h);
+  const __half2 m = __hmax2(*reinterpret_cast<const __half2*>(&rng), h);
+  rng = *reinterpret_cast<const uint32_t*>(&m);
 }
 
-// 16 accumulator columns [c0, c0+16) of one row: +bias, (alpha head), ReLU, pack, two swizzled 16-byte stores
-template <bool RELU, bool ALPHA>
-__device__ __forceinline__ uint32_t epi_sub16(const uint32_t (&v)[16], const float4 (&b)[4], const float (&aw)[8], int c0,
-                                          float (&alpha)[4], uint8_t* act, int row, __half* grow) {
+template <bool RELU, bool ALPHA, bool kParam, bool kRange>
+__device__ __forceinline__ uint32_t epi_sub16(const TcParams& P, const uint32_t (&v)[16], int c0, float (&alpha)[4],
+                                          uint8_t* act, int row, uint32_t& rng) {
   uint32_t packed[8];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    float x0 = __uint_as_float(v[4 * g + 0]) + b[g].x, x1 = __uint_as_float(v[4 * g + 1]) + b[g].y;
-    float x2 = __uint_as_float(v[4 * g + 2]) + b[g].z, x3 = __uint_as_float(v[4 * g + 3]) + b[g].w;
+    const float x0 = __uint_as_float(v[4 * g + 0]), x1 = __uint_as_float(v[4 * g + 1]);      // bias included by the MMAs
+    const float x2 = __uint_as_float(v[4 * g + 2]), x3 = __uint_as_float(v[4 * g + 3]);
     if (ALPHA) {                                // alpha_linear on the fp32 ReLU output (:135)
-      // column c = c0 + 4g + j lives in lane c/8, register c%8
-      const int src = (c0 >> 3) + (g >> 1), r0 = (g & 1) * 4;
-      alpha[0] = fmaf(fmaxf(x0, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 0], src), alpha[0]);
-      alpha[1] = fmaf(fmaxf(x1, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 1], src), alpha[1]);
-      alpha[2] = fmaf(fmaxf(x2, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 2], src), alpha[2]);
-      alpha[3] = fmaf(fmaxf(x3, 0.f), __shfl_sync(0xffffffffu, aw[r0 + 3], src), alpha[3]);
+      const float4 w = cst4<kParam>(P, TC_CONST_ALPHA + c0 + 4 * g);
+      alpha[0] = fmaf(fmaxf(x0, 0.f), w.x, alpha[0]);
+      alpha[1] = fmaf(fmaxf(x1, 0.f), w.y, alpha[1]);
+      alpha[2] = fmaf(fmaxf(x2, 0.f), w.z, alpha[2]);
+      alpha[3] = fmaf(fmaxf(x3, 0.f), w.w, alpha[3]);
     }
     packed[2 * g] = pack2<RELU>(x0, x1);
     packed[2 * g + 1] = pack2<RELU>(x2, x3);
+  }
+  if (kRange) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) track_range<RELU>(rng, packed[j]);
   }
   uint8_t* blk = act + (c0 >> 6) * TC_KB_BYTES + row * 128;
   const int ch0 = (c0 & 63) >> 3;
   *reinterpret_cast<uint4*>(blk + ((ch0 ^ (row & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   *reinterpret_cast<uint4*>(blk + (((ch0 + 1) ^ (row & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-  if (grow) {                                   // training: stash the activations for the backward pass
-    *reinterpret_cast<uint4*>(grow + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    *reinterpret_cast<uint4*>(grow + c0 + 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-  }
   // ReLU sign word of these 16 outputs (training kernel only): bit j = [column c0+2j > 0], bit 8+j = [column
   // c0+2j+1 > 0].  The INT32 pipe runs at half the FP rate and this epilogue is short of issue slots in the training
   // kernel, so the compare is a packed-half HSET2 (one per register, FP16 pipe) that yields 0xFFFF per positive half,
@@ -226,31 +244,24 @@ __device__ __forceinline__ uint32_t epi_sub16(const uint32_t (&v)[16], const flo
   return __byte_perm(acc, 0u, 0x4420);          // byte 0 = low halves, byte 1 = high halves
 }
 
-// Drains `ncols` accumulator columns of this thread's TMEM lane into the activation block, software
-// pipelined over 16-column sub-chunks: the tcgen05.ld and the bias loads of sub-chunk i+1 are in flight
-// while sub-chunk i is converted and stored.
-template <bool RELU, bool ALPHA, bool kConst>
-__device__ __forceinline__ void epi_step(uint32_t t_lane, int cbase, int ncols, const float* sbias, int cbias,
-                                         const float (&aw)[8], float (&alpha)[4], uint8_t* act, int row, __half* grow,
-                                         uint4& signs) {
+// Drains NC accumulator columns [CB, CB + NC) of this thread's TMEM lane into the activation block, fully unrolled
+// (every column offset is a compile-time constant) and software pipelined over 16-column sub-chunks: the tcgen05.ld
+// of sub-chunk i+1 is in flight while sub-chunk i is converted and stored.
+template <bool RELU, bool ALPHA, int CB, int NC, bool kParam, bool kRange>
+__device__ __forceinline__ void epi_step(const TcParams& P, uint32_t t_lane, float (&alpha)[4], uint8_t* act, int row,
+                                         uint4& signs, uint32_t& rng) {
   uint32_t v0[16], v1[16];
-  float4 b0[4], b1[4];
-  tmem_ld16(t_lane + cbase, v0);
-  load_bias16<kConst>(b0, sbias + cbase, cbias + cbase);
-#pragma unroll 1
-  for (int c = cbase; c < cbase + ncols; c += 32) {
+  tmem_ld16(t_lane + CB, v0);
+#pragma unroll
+  for (int q = 0; q < NC / 32; ++q) {
+    const int c = CB + 32 * q;
     tmem_wait_ld();
     tmem_ld16(t_lane + c + 16, v1);
-    load_bias16<kConst>(b1, sbias + c + 16, cbias + c + 16);
-    const uint32_t m0 = epi_sub16<RELU, ALPHA>(v0, b0, aw, c, alpha, act, row, grow);
+    const uint32_t m0 = epi_sub16<RELU, ALPHA, kParam, kRange>(P, v0, c, alpha, act, row, rng);
     tmem_wait_ld();
-    if (c + 32 < cbase + ncols) {
-      tmem_ld16(t_lane + c + 32, v0);
-      load_bias16<kConst>(b0, sbias + c + 32, cbias + c + 32);
-    }
-    const uint32_t m1 = epi_sub16<RELU, ALPHA>(v1, b1, aw, c + 16, alpha, act, row, grow);
+    if (q + 1 < NC / 32) tmem_ld16(t_lane + c + 32, v0);
+    const uint32_t m1 = epi_sub16<RELU, ALPHA, kParam, kRange>(P, v1, c + 16, alpha, act, row, rng);
     const uint32_t w = m0 | (m1 << 16);
-    const int q = (c - cbase) >> 5;
     if (q == 0) signs.x = w; else if (q == 1) signs.y = w; else if (q == 2) signs.z = w; else signs.w = w;
   }
 }
@@ -265,12 +276,12 @@ __device__ __forceinline__ void epi_step(uint32_t t_lane, int cbase, int ncols, 
     if (P.trace && blockIdx.x < 2 && (idx) < 256) P.trace[((blockIdx.x * 2 + (role)) * 4 + (ev)) * 256 + (idx)] = clock64(); \
   } while (0)
 
-template <int kPair, bool kConst, bool kTrain>
+template <int kPair, bool kTrain, bool kRange>
 __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __grid_constant__ TcParams P) {
   using C = TcCfg<kPair>;
   constexpr int NT = C::NT, NSLOT = C::NSLOT;
+  constexpr bool kParam = !kTrain;               // where the constant table comes from (see TcParams::consts)
   extern __shared__ uint8_t smem_dyn[];
-  // 1024-byte alignment (SWIZZLE_128B atoms); identical offset in both CTAs of a pair
   // SWIZZLE_128B atoms need a 1024-byte aligned base (identical in both CTAs of a pair)
   const uint32_t raw_addr = smem_u32(smem_dyn);
   const uint32_t pad = (1024 - (raw_addr & 1023)) & 1023;
@@ -278,7 +289,9 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
   uint8_t* smem = smem_dyn + pad;
   const uint32_t sbase = smem_u32(smem);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index broadcast from lane 0: tells the compiler it is warp-uniform, so role branches are uniform branches and
+  // step-dependent constant-bank addresses can live in uniform registers (LDCU / FADD R, R, UR in the epilogue)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   const uint32_t rank = kPair == 2 ? cluster_ctarank() : 0;
   const long long pair_id = blockIdx.x / kPair;
   const long long n_pairs = gridDim.x / kPair;
@@ -289,17 +302,24 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
   auto bar_tfull = [&](int t) { return sbase + C::OFF_BAR + 8 * (3 * NSLOT + t); };
   auto bar_aready = [&](int t) { return sbase + C::OFF_BAR + 8 * (3 * NSLOT + NT + t); };
   const uint32_t bar_pefree = sbase + C::OFF_BAR + 8 * (3 * NSLOT + 2 * NT);
+  const uint32_t bar_peready = sbase + C::OFF_BAR + 8 * (3 * NSLOT + 2 * NT + 1);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEMPTR);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(bar_full(i), 1); mbar_init(bar_peer(i), 1); mbar_init(bar_empty(i), 1); }
     for (int t = 0; t < NT; ++t) { mbar_init(bar_tfull(t), 1); mbar_init(bar_aready(t), 8 * kPair); }
     mbar_init(bar_pefree, 1);
+    mbar_init(bar_peready, 4 * kPair);
     fence_mbar_init();
   }
   if (warp == 1) {
     tmem_alloc<kPair>(smem_u32(tmem_ptr_smem), 512);
     tmem_relinquish<kPair>();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 80) {           // 16 rows of 16 bytes: the first 8 carry the two ones
+    const int r = threadIdx.x - 64;
+    *reinterpret_cast<uint4*>(smem + C::OFF_ONES + 16 * r) = r < 8 ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -309,6 +329,13 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
 
   const long long tiles_per_round = n_pairs * NT;
   const long long n_rounds = (P.n_tiles + tiles_per_round - 1) / tiles_per_round;
+  // sample handled by row `r` of this CTA in tile t of a round
+  auto sample_of = [&](long long round, int t, int r) { return (((round * n_pairs + pair_id) * NT + t) * kPair + rank) * 128 + r; };
+  auto valid_of = [&](long long round, int t, int r) {
+    return ((round * n_pairs + pair_id) * NT + t) < P.n_tiles && sample_of(round, t, r) < P.in.n;
+  };
+  // PE-buffer use index (order of the MMA stream: per round tile0/tile1 at step 0, then at step 5, then at step 9)
+  auto pe_use = [&](long long round, int k, int t) { return (round * 3 + k) * NT + t; };
 
   if (warp == 0) {
     // =============================== bulk-TMA producer ===============================
@@ -317,8 +344,8 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
       uint32_t q = 0;
       for (long long round = 0; round < n_rounds; ++round) {
         for (int s = 0; s < TC_STEPS; ++s) {
-          const uint32_t bytes = P.plan.slab_bytes[s];
           for (int kb = 0; kb < step_nkb(s); ++kb, ++q) {
+            const uint32_t bytes = kb_is_bias(s, kb) ? P.plan.slab_bytes[s] / 4 : P.plan.slab_bytes[s];
             const uint32_t slot = q % NSLOT, gen = q / NSLOT;
             mbar_wait(bar_empty(slot), (gen & 1) ^ 1);
             mbar_arrive_expect_tx(bar_full(slot), bytes);
@@ -340,6 +367,7 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
         for (int s = 0; s < TC_STEPS; ++s, ++nstep) {
           const uint32_t idesc = make_idesc(128 * kPair, step_N(s));
           const int nkb = step_nkb(s);
+          const int pe_k = s == 0 ? 0 : (s == 5 ? 1 : 2);
           for (int t = 0; t < NT; ++t) {
             mbar_wait(bar_aready(t), nstep & 1);          // A operand written, accumulator drained
             tc_fence_after();
@@ -352,18 +380,29 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
                 if (kPair == 2) mbar_wait(bar_peer(slot), gen & 1);
                 tc_fence_after();
               }
-              const bool is_pe = kb_is_pe(s, kb);
+              const bool is_pe = kb_is_pe(s, kb), is_bias = kb_is_bias(s, kb);
+              if (is_pe) {                                // encodings written by the encoding warps of both CTAs
+                mbar_wait(bar_peready, (uint32_t)(pe_use(round, pe_k, t) & 1));
+                tc_fence_after();
+              }
               const uint32_t a_addr = is_pe ? sbase + C::OFF_PE
                                             : sbase + C::OFF_ACT + (t * 4 + kb_act_index(s, kb)) * TC_KB_BYTES;
               const uint64_t a_desc = make_desc(a_addr);
               const uint64_t b_desc = make_desc(sbase + C::OFF_RING + slot * C::SLOT_BYTES);
               if (issuer) {
-                // K advances by 32 B (= 2 in descriptor address units) inside the 128-byte swizzle atom
-                umma_f16<kPair>(d_tmem, a_desc, b_desc, idesc, kb != 0);
-                umma_f16<kPair>(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
-                if (kb_ksteps(s, kb) == 4) {
-                  umma_f16<kPair>(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
-                  umma_f16<kPair>(d_tmem, a_desc + 6, b_desc + 6, idesc, 1);
+                if (is_bias) {
+                  // D += ones[128 x 16] . bias_slab[N x 16]^T: both operands K-major without swizzle (core matrices of
+                  // 8 rows x 16 B, 128 B apart along K); A: zero stride between row groups, B: 256 B between row groups
+                  umma_f16<kPair>(d_tmem, make_desc_ns(sbase + C::OFF_ONES, 128, 0),
+                                  make_desc_ns(sbase + C::OFF_RING + slot * C::SLOT_BYTES, 128, 256), idesc, 1);
+                } else {
+                  // K advances by 32 B (= 2 in descriptor address units) inside the 128-byte swizzle atom
+                  umma_f16<kPair>(d_tmem, a_desc, b_desc, idesc, kb != 0);
+                  umma_f16<kPair>(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
+                  if (kb_ksteps(s, kb) == 4) {
+                    umma_f16<kPair>(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
+                    umma_f16<kPair>(d_tmem, a_desc + 6, b_desc + 6, idesc, 1);
+                  }
                 }
                 if (t == NT - 1) umma_commit<kPair>(bar_empty(slot));      // slab consumed by every tile
                 if (is_pe) umma_commit<kPair>(bar_pefree);                 // PE block may be rewritten
@@ -393,81 +432,84 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
             }
       }
     }
+  } else if (warp >= 10) {
+    // ========================= encoding warps: one thread per sample row =========================
+    // Embedder.forward (models/vanilla.py:82-92) of the samples, well ahead of the MMAs that read it: the fp16
+    // encodings of both tiles of a round live in these threads' registers and are stored into the (single) PE block
+    // in the order the MMA stream uses it -- tile 0 / tile 1 at step 0, again at step 5 (skip connection, :131), the
+    // direction encoding at step 9 (:137) -- each store waiting for the MMAs of the previous use to retire.
+    const int prow = (warp - 10) * 32 + lane;
+    uint8_t* pebuf = smem + C::OFF_PE;
+    uint32_t pos[NT][32], dir[NT][16];
+    uint32_t rng = 0;
+    auto encode_pos = [&](long long round) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
+        if (valid_of(round, t, prow)) nm_fetch_sample(P.in, sample_of(round, t, prow), p, v);
+        encode_f16(P.pos_pe, p, pos[t], 30);
+        if (kRange) track_range<false>(rng, pos[t][0]), track_range<false>(rng, pos[t][1]);   // raw x, y, z (+ one sine)
+      }
+    };
+    auto encode_dir = [&](long long round) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
+        if (valid_of(round, t, prow)) nm_fetch_sample(P.in, sample_of(round, t, prow), p, v);
+        uint32_t tmp[32];
+        encode_f16(P.dir_pe, v, tmp, 12);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dir[t][j] = tmp[j];
+        if (kRange) track_range<false>(rng, tmp[0]), track_range<false>(rng, tmp[1]);
+      }
+    };
+    auto put = [&](long long u, const uint32_t* v, int nchunks) {
+      if (u > 0) mbar_wait_backoff(bar_pefree, (uint32_t)((u - 1) & 1), 32);
+      store_row_swizzled(pebuf, prow, v, nchunks);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(bar_peready, 0);
+    };
+    if (n_rounds > 0) encode_pos(0);
+    for (long long round = 0; round < n_rounds; ++round) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) put(pe_use(round, 0, t), pos[t], 8);
+      encode_dir(round);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) put(pe_use(round, 1, t), pos[t], 8);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) put(pe_use(round, 2, t), dir[t], 4);
+      if (round + 1 < n_rounds) encode_pos(round + 1);
+    }
+    if (kRange && (((rng & 0xFFFFu) >= 0x7BFFu) || ((rng >> 16) >= 0x7BFFu))) atomicOr(P.range_flag, 1);
   } else {
     // ========================= epilogue: 8 warps serve the tiles in flight in turn =========================
     // Both warpgroups drain every tile: warp (2+q) and warp (6+q) share TMEM lane quadrant q and split the
-    // accumulator columns in halves (g = 0 / 1), so a step's epilogue takes half as long.  Warpgroup g also
-    // owns the encodings (registers) of tile g and stores them into the PE block at that tile's steps 0/5/9.
+    // accumulator columns in halves (g = 0 / 1), so a step's epilogue takes half as long.
     const int ew = warp - 2;                       // 0..7
-    const int g = ew >> 2;                         // column half; tile whose encodings this thread owns
+    const int g = ew >> 2;                         // column half
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;              // sample row inside the CTA tile
     const int etid = ew * 32 + lane;               // 0..255
-    uint8_t* pebuf = smem + C::OFF_PE;
-    float* sbias = reinterpret_cast<float*>(smem + C::OFF_BIAS);           // current step's bias row (256 fp32)
-    float* s_alpha = sbias + 256;                                          // [NT][128] alpha partial of the g==1 half
-    float aw[8];                                                           // alpha weights 8*lane .. 8*lane+7
-#pragma unroll
-    for (int k = 0; k < 8; ++k) aw[k] = __ldg(P.bias + 11 * TC_BIAS_STRIDE + 8 * lane + k);
-    const float4 rgb_bias = __ldg(reinterpret_cast<const float4*>(P.bias + 10 * TC_BIAS_STRIDE));   // + alpha bias in .w
+    float* s_alpha = reinterpret_cast<float*>(smem + C::OFF_ALPHA);        // [NT][128] alpha partial of the g==1 half
     uint32_t nstep = 0;
+    uint32_t rng = 0;
 
-    auto epi_barrier = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     auto publish = [&](int t) {                     // tile t: A operand ready + accumulator drained
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(bar_aready(t), 0);
     };
-    // PE-buffer use index u (order of the MMA stream: per round A0,B0,A5,B5,A9,B9); the writer of use u
-    // waits until the MMAs of use u-1 have retired
-    auto wait_pe_slot = [&](long long round, int k, int t) {
-      long long u = (round * 3 + k) * NT + t;
-      if (u > 0) mbar_wait(bar_pefree, (uint32_t)((u - 1) & 1));
-    };
-    auto sample_index = [&](long long round, int t) { return (((round * n_pairs + pair_id) * NT + t) * kPair + rank) * 128 + row; };
-    auto tile_valid = [&](long long round, int t) {
-      return ((round * n_pairs + pair_id) * NT + t) < P.n_tiles && sample_index(round, t) < P.in.n;
-    };
-    // The encodings of tile g live in this thread's registers.  The position encoding of the NEXT round is
-    // computed in the shadow of step 6's MMAs (its registers are dead after step 5), the direction encoding of
-    // the current round in the shadow of step 7's, so only the very first tile pays for them up front.
-    const bool pe_owner = g < NT;
-    uint32_t pe_pos[32], pe_dir[16];
-    auto encode_pos = [&](long long round) {
-      float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
-      if (tile_valid(round, g)) nm_fetch_sample(P.in, sample_index(round, g), p, v);
-      encode_f16(P.pos_pe, p, pe_pos, 30);
-    };
-    auto encode_dir = [&](long long round) {
-      float p[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
-      if (tile_valid(round, g)) nm_fetch_sample(P.in, sample_index(round, g), p, v);
-      uint32_t tmp[32];
-      encode_f16(P.dir_pe, v, tmp, 12);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) pe_dir[j] = tmp[j];
-    };
-    if (n_rounds > 0 && pe_owner) encode_pos(0);
-    if (!kConst) {
-      sbias[etid] = __ldg(P.bias + etid);          // bias row of step 0
-      epi_barrier();
-    }
 
     for (long long round = 0; round < n_rounds; ++round) {
-      // ---- step 0 inputs: positional encoding blocks ----
-      for (int t = 0; t < NT; ++t) {
-        if (g == t) {
-          wait_pe_slot(round, 0, t);
-          store_row_swizzled(pebuf, row, pe_pos, 8);
-        }
-        publish(t);
-      }
+      // ---- step 0 reads only the PE block: nothing to drain, the tiles' accumulators are free ----
+#pragma unroll
+      for (int t = 0; t < NT; ++t) publish(t);
       float alpha[NT][4];
 #pragma unroll
       for (int t = 0; t < NT; ++t) alpha[t][0] = alpha[t][1] = alpha[t][2] = alpha[t][3] = 0.f;
       for (int s = 0; s < TC_STEPS; ++s, ++nstep) {
-        const float next_bias = (!kConst && s < 10) ? __ldg(P.bias + ((s + 1) % 10) * TC_BIAS_STRIDE + etid) : 0.f;
-        const int cbias = P.cslot * TC_BIAS_FLOATS + s * TC_BIAS_STRIDE;
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           uint8_t* act = smem + C::OFF_ACT + t * 4 * TC_KB_BYTES;
@@ -476,29 +518,33 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
           tc_fence_after();
           if (t == 0 && etid == 0) TC_TRACE(1, 0, nstep);
           if (s < 10) {
-            const int nh = (s == 9) ? 64 : 128;         // columns drained by this thread
-            __half* grow = nullptr;                     // per-thread HBM stores: unused, the stash goes out by TMA below
-            // this warp's slice of the tile's activation buffer is the source of the TMA store issued one step
-            // ago: it must have been read before the slice is overwritten (the other tile's store may still fly)
+            // training: this warp's slice of the tile's activation buffer is the source of the TMA store issued one
+            // step ago: it must have been read before the slice is overwritten (the other tile's store may still fly)
             if (kTrain) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
             uint4 signs = make_uint4(0, 0, 0, 0);
-            if (s == 7) epi_step<true, true, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row, grow, signs);
-            else if (s == 8) epi_step<false, false, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row, grow, signs);
-            else epi_step<true, false, kConst>(t_lane, g * nh, nh, sbias, cbias, aw, alpha[t], act, row, grow, signs);
-            if (kTrain && s < 8 && tile_valid(round, t))
-              reinterpret_cast<uint4*>(P.st_m + ((size_t)s * P.in.n + sample_index(round, t)) * 8)[g] = signs;
-            if (kTrain && s == 9 && tile_valid(round, t))   // views layer: 64 columns per thread -> words 2g, 2g+1 of plane 8
-              reinterpret_cast<uint2*>(P.st_m + ((size_t)8 * P.in.n + sample_index(round, t)) * 8)[g] = make_uint2(signs.x, signs.y);
+            if (g == 0) {
+              if (s == 7) epi_step<true, true, 0, 128, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
+              else if (s == 8) epi_step<false, false, 0, 128, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
+              else if (s == 9) epi_step<true, false, 0, 64, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
+              else epi_step<true, false, 0, 128, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
+            } else {
+              if (s == 7) epi_step<true, true, 128, 128, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
+              else if (s == 8) epi_step<false, false, 128, 128, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
+              else if (s == 9) epi_step<true, false, 64, 64, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
+              else epi_step<true, false, 128, 128, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
+            }
+            if (kTrain && s < 8 && valid_of(round, t, row))
+              reinterpret_cast<uint4*>(P.st_m + ((size_t)s * P.in.n + sample_of(round, t, row)) * 8)[g] = signs;
+            if (kTrain && s == 9 && valid_of(round, t, row))   // views layer: 64 columns per thread -> words 2g, 2g+1 of plane 8
+              reinterpret_cast<uint2*>(P.st_m + ((size_t)8 * P.in.n + sample_of(round, t, row)) * 8)[g] = make_uint2(signs.x, signs.y);
             if (s == 7 && g == 1) s_alpha[t * 128 + row] = (alpha[t][0] + alpha[t][1]) + (alpha[t][2] + alpha[t][3]);
-            if (s == 4 && g == t) { wait_pe_slot(round, 1, t); store_row_swizzled(pebuf, row, pe_pos, 8); }   // skip input (:131)
-            if (s == 8 && g == t) { wait_pe_slot(round, 2, t); store_row_swizzled(pebuf, row, pe_dir, 4); }   // view dirs (:137)
             if (t == 0 && etid == 0) TC_TRACE(1, 1, nstep);
             if (kTrain) {
               // activation stash: this warp's 32 rows x (128 | 64) columns leave by TMA straight from the swizzled
               // A buffer.  Steps 0..7: the MMA thread is told first (the store and the next step's MMAs only read the
               // slice).  Steps 8 and 9 hand the slice to another warp (the column split changes from 128 to 64 per
               // warpgroup and back), so there the store must have finished reading before anyone goes on.
-              const long long i0 = sample_index(round, t) - lane;            // first row of this warp
+              const long long i0 = sample_of(round, t, row) - lane;            // first row of this warp
               const bool issue = lane == 0 && i0 < P.in.n && !(P.dbg & 1);
               const uint32_t src = sbase + C::OFF_ACT + t * 4 * TC_KB_BYTES + quad * 32 * 128;
               if (s < 8) {
@@ -532,29 +578,20 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
               uint32_t v[4];
               tmem_ld4(t_lane + 128, v);
               tmem_wait_ld();
-              const long long i = sample_index(round, t);
-              if (tile_valid(round, t)) {
+              if (valid_of(round, t, row)) {
                 const float a = (alpha[t][0] + alpha[t][1]) + (alpha[t][2] + alpha[t][3]) + s_alpha[t * 128 + row];
-                float4 o = make_float4(__uint_as_float(v[0]) + rgb_bias.x, __uint_as_float(v[1]) + rgb_bias.y,
-                                       __uint_as_float(v[2]) + rgb_bias.z, a + rgb_bias.w);
-                reinterpret_cast<float4*>(P.raw)[i] = o;                     // [r,g,b,sigma] (:144)
+                const float4 ob = cst4<kParam>(P, TC_CONST_OUT);
+                float4 o = make_float4(__uint_as_float(v[0]) + ob.x, __uint_as_float(v[1]) + ob.y,
+                                       __uint_as_float(v[2]) + ob.z, a + ob.w);
+                reinterpret_cast<float4*>(P.raw)[sample_of(round, t, row)] = o;   // [r,g,b,sigma] (:144)
               }
             }
             tc_fence_before();
           }
         }
-        if (s < 10) {
-          // next step's bias row: every epilogue thread is done reading the current one after this barrier
-          if (!kConst) {
-            epi_barrier();
-            sbias[etid] = next_bias;
-            epi_barrier();
-          }
-          if (s == 5 && round + 1 < n_rounds && pe_owner) encode_pos(round + 1);
-          if (s == 6 && pe_owner) encode_dir(round);
-        }
       }
     }
+    if (kRange && (((rng & 0xFFFFu) >= 0x7BFFu) || ((rng >> 16) >= 0x7BFFu))) atomicOr(P.range_flag, 1);
   }
 
   // ---- teardown ----
@@ -572,6 +609,7 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
 // ---------------------------------------------------------------------------------------------
 struct PackSrc {
   const float* w[8]; const float* feat; const float* views; const float* rgb;
+  const float* b[8]; const float* feat_b; const float* views_b;      // biases: they ride in the slabs (column of the constant-1 channel)
 };
 
 // weight of (step s, output n, k-block kb, kk in [0,64)) or 0 for padding
@@ -589,8 +627,12 @@ __device__ __forceinline__ float src_weight(const PackSrc& S, int s, int n, int 
     if (kb < 4) return S.views[(size_t)n * ld + kb * 64 + kk];
     return kk < NM_DIR_PE ? S.views[(size_t)n * ld + 256 + kk] : 0.f;
   }
-  // s == 10: rgb, N padded 3 -> 16
+  // s == 10: rgb, N padded 3 -> 16 (its bias is added with the alpha bias when the output is written)
   return n < 3 ? S.rgb[(size_t)n * 128 + kb * 64 + kk] : 0.f;
+}
+
+__device__ __forceinline__ float src_bias(const PackSrc& S, int s, int n) {
+  return s <= 7 ? S.b[s][n] : (s == 8 ? S.feat_b[n] : S.views_b[n]);
 }
 
 __global__ void k_tc_pack(PackSrc S, TcPlan plan, int kpair, __half* __restrict__ out) {
@@ -605,25 +647,29 @@ __global__ void k_tc_pack(PackSrc S, TcPlan plan, int kpair, __half* __restrict_
     for (int k = 0; k < step_nkb(ss); ++k)
       if (byte >= plan.slab_off[ss][k]) { s = ss; kb = k; }
   const uint32_t in_slab = byte - plan.slab_off[s][kb];
+  const int n_cta = step_N(s) / kpair;
+  if (kb_is_bias(s, kb)) {
+    // K-major, no swizzle: [n / 8][k / 8][n % 8][k % 8] halves; k = 0: fp16(b), k = 1: fp16(b - fp16(b)), else 0
+    const int n_local = (in_slab >> 8) * 8 + ((in_slab & 127) >> 4);
+    const int kk = ((in_slab >> 7) & 1) * 8 + ((in_slab & 15) >> 1);
+    const float b = src_bias(S, s, rank * n_cta + n_local);
+    const __half hi = __float2half_rn(b);
+    out[(size_t)rank * (plan.image_bytes / 2) + e] = kk == 0 ? hi : (kk == 1 ? __float2half_rn(b - __half2float(hi)) : __float2half_rn(0.f));
+    return;
+  }
   const int n_local = in_slab >> 7;
   const int chunk_phys = (in_slab & 127) >> 4;
   const int chunk = chunk_phys ^ (n_local & 7);                         // undo the 128B swizzle
   const int kk = chunk * 8 + ((in_slab & 15) >> 1);
-  const int n_cta = step_N(s) / kpair;
   const int n = rank * n_cta + n_local;
   out[(size_t)rank * (plan.image_bytes / 2) + e] = __float2half_rn(src_weight(S, s, n, kb, kk));
 }
 
-__global__ void k_tc_bias(const float* b0, const float* b1, const float* b2, const float* b3, const float* b4,
-                          const float* b5, const float* b6, const float* b7, const float* feat_b, const float* views_b,
-                          const float* rgb_b, const float* alpha_w, const float* alpha_b, float* __restrict__ out) {
+// the constant table of the epilogue (layout: TcParams::consts)
+__global__ void k_tc_consts(const float* rgb_b, const float* alpha_w, const float* alpha_b, float* __restrict__ out) {
   const int i = threadIdx.x;      // 256 threads
-  const float* bs[8] = {b0, b1, b2, b3, b4, b5, b6, b7};
-  for (int s = 0; s < 8; ++s) out[s * TC_BIAS_STRIDE + i] = bs[s][i];
-  out[8 * TC_BIAS_STRIDE + i] = feat_b[i];
-  out[9 * TC_BIAS_STRIDE + i] = i < 128 ? views_b[i] : 0.f;
-  out[10 * TC_BIAS_STRIDE + i] = i < 3 ? rgb_b[i] : (i == 3 ? alpha_b[0] : 0.f);
-  out[11 * TC_BIAS_STRIDE + i] = alpha_w[i];
+  out[TC_CONST_ALPHA + i] = alpha_w[i];
+  if (i < TC_CONST_FLOATS - TC_CONST_OUT) out[TC_CONST_OUT + i] = i < 3 ? rgb_b[i] : (i == 3 ? alpha_b[0] : 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -676,7 +722,7 @@ static TcPlan make_plan(int kpair) {
   uint32_t off = 0;
   for (int s = 0; s < TC_STEPS; ++s) {
     p.slab_bytes[s] = (uint32_t)(step_N(s) / kpair) * 128u;
-    for (int kb = 0; kb < step_nkb(s); ++kb) { p.slab_off[s][kb] = off; off += p.slab_bytes[s]; }
+    for (int kb = 0; kb < step_nkb(s); ++kb) { p.slab_off[s][kb] = off; off += kb_is_bias(s, kb) ? p.slab_bytes[s] / 4 : p.slab_bytes[s]; }
   }
   p.image_bytes = off;
   return p;
@@ -693,31 +739,26 @@ int nm_tc_pack(nm_ctx* ctx, NmNet& net, cudaStream_t st) {
     NM_CHECK_CUDA(ctx, cudaMalloc(&net.f16, halfs * sizeof(__half)));
     net.f16_halfs = halfs;
   }
-  if (!net.tc_bias) NM_CHECK_CUDA(ctx, cudaMalloc(&net.tc_bias, TC_BIAS_FLOATS * sizeof(float)));
+  if (!net.tc_bias) NM_CHECK_CUDA(ctx, cudaMalloc(&net.tc_bias, TC_CONST_FLOATS * sizeof(float)));
   const nm_nerf_desc& d = net.desc;
   PackSrc S;
   for (int l = 0; l < 8; ++l) S.w[l] = d.pts_w[l];
   S.feat = d.feature_w; S.views = d.views_w; S.rgb = d.rgb_w;
+  for (int l = 0; l < 8; ++l) S.b[l] = d.pts_b[l];
+  S.feat_b = d.feature_b; S.views_b = d.views_b;
   dim3 grid((unsigned)((plan.image_bytes / 2 + 255) / 256), kpair);
   k_tc_pack<<<grid, 256, 0, st>>>(S, plan, kpair, net.f16);
   NM_CHECK_LAUNCH(ctx);
-  k_tc_bias<<<1, 256, 0, st>>>(d.pts_b[0], d.pts_b[1], d.pts_b[2], d.pts_b[3], d.pts_b[4], d.pts_b[5], d.pts_b[6],
-                               d.pts_b[7], d.feature_b, d.views_b, d.rgb_b, d.alpha_w, d.alpha_b, net.tc_bias);
+  k_tc_consts<<<1, 256, 0, st>>>(d.rgb_b, d.alpha_w, d.alpha_b, net.tc_bias);
   NM_CHECK_LAUNCH(ctx);
-  {
-    const int slot = (int)(&net - ctx->nets);
-    if (slot >= 0 && slot < TC_CONST_NETS)
-      NM_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tc_bias, net.tc_bias, TC_BIAS_FLOATS * sizeof(float),
-                                                 (size_t)slot * TC_BIAS_FLOATS * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  }
-
+  net.consts_host_valid = false;        // the host copy (kernel parameters of inference launches) is refreshed lazily
   return NM_OK;
 }
 
-template <int kPair, bool kConst, bool kTrain>
+template <int kPair, bool kTrain, bool kRange>
 static int launch_tc(nm_ctx* ctx, const TcParams& P, cudaStream_t st) {
   using C = TcCfg<kPair>;
-  NM_SET_SMEM_ONCE(ctx, (k_mlp_tc<kPair, kConst, kTrain>), C::SMEM_BYTES);
+  NM_SET_SMEM_ONCE(ctx, (k_mlp_tc<kPair, kTrain, kRange>), C::SMEM_BYTES);
   int ctas = ctx->sm_count - (ctx->sm_count % kPair);
   long long need = P.n_tiles * kPair;                       // CTAs that have work in the first round
   need = (need + C::NT - 1) / C::NT;
@@ -733,19 +774,18 @@ static int launch_tc(nm_ctx* ctx, const TcParams& P, cudaStream_t st) {
   attr[0].val.clusterDim.x = kPair; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NM_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_mlp_tc<kPair, kConst, kTrain>, P));
+  NM_CHECK_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_mlp_tc<kPair, kTrain, kRange>, P));
   NM_LAUNCHED(ctx);
   return NM_OK;
 }
 
-int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* views, const float* origins,
+int nm_tc_forward(nm_ctx* ctx, NmNet& net, const float* pts, const float* views, const float* origins,
                   const float* dirs, const float* z, int64_t n, int32_t group, float* raw, cudaStream_t st,
                   const NmTrainStash* stash) {
   const int kpair = tc_pair_mode();
   if (!net.f16 || !net.tc_bias) NM_FAIL(ctx, NM_ERR_STATE, "nm_tc_forward: weights not packed");
   TcParams P;
   P.wimg = reinterpret_cast<const uint8_t*>(net.f16);
-  P.bias = net.tc_bias;
   P.plan = make_plan(kpair);
   P.in = NmMlpInput{pts, views, origins, dirs, z, (long long)n, group};
   P.pos_pe = NmPeSpec{net.desc.pos_pe_kind, net.desc.pos_n_freqs, net.f32 + net.o_pos_cyc};
@@ -754,6 +794,7 @@ int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* 
   P.n_tiles = (n + 128 * kpair - 1) / (128 * kpair);
   P.trace = nullptr;
   P.dbg = 0;
+  P.range_flag = ctx->d_counter + NM_RANGE_FLAG_WORD;
   if (const char* e = getenv("NEUMAN_TC_DEBUG")) P.dbg = atoi(e);
   P.st_x = stash ? stash->x : nullptr; P.st_f = stash ? stash->f : nullptr; P.st_v = stash ? stash->v : nullptr;
   P.st_m = stash ? stash->m : nullptr;
@@ -763,12 +804,24 @@ int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* 
     if (tc_make_store_map(&P.map_x, stash->x, 8, (uint64_t)n, 256) || tc_make_store_map(&P.map_f, stash->f, 1, (uint64_t)n, 256) ||
         tc_make_store_map(&P.map_v, stash->v, 1, (uint64_t)n, 128))
       NM_FAIL(ctx, NM_ERR_CUDA, "nm_mlp_forward_train: cuTensorMapEncodeTiled failed");
+    // training forward: the constant table stays on the device (stream-ordered copy into the __constant__ bank)
+    NM_CHECK_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tc_consts, net.tc_bias, TC_CONST_FLOATS * sizeof(float), 0,
+                                               cudaMemcpyDeviceToDevice, st));
+  } else {
+    if (!net.consts_host_valid) {       // once per (re)pack: the constant table becomes kernel parameters
+      if (!net.consts_host) NM_CHECK_CUDA(ctx, cudaMallocHost(&net.consts_host, TC_CONST_FLOATS * sizeof(float)));
+      NM_CHECK_CUDA(ctx, cudaMemcpyAsync(net.consts_host, net.tc_bias, TC_CONST_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, st));
+      NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+      net.consts_host_valid = true;
+    }
+    memcpy(P.consts, net.consts_host, sizeof(P.consts));
   }
   if (const char* e = getenv("NEUMAN_TC_TRACE")) P.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
-  const int slot = (int)(&net - ctx->nets);
-  P.cslot = (slot >= 0 && slot < TC_CONST_NETS) ? slot : 0;
-  if (slot >= 0 && slot < TC_CONST_NETS && getenv("NEUMAN_TC_CONST_BIAS"))   // measured slower than the smem row (1.18 vs 1.45 PFLOP/s): opt-in only
+  static const bool range_on = !(getenv("NEUMAN_TC_RANGE") && getenv("NEUMAN_TC_RANGE")[0] == '0');
+  if (P.st_x) {
+    if (range_on) return kpair == 2 ? launch_tc<2, true, true>(ctx, P, st) : launch_tc<1, true, true>(ctx, P, st);
     return kpair == 2 ? launch_tc<2, true, false>(ctx, P, st) : launch_tc<1, true, false>(ctx, P, st);
-  if (P.st_x) return kpair == 2 ? launch_tc<2, false, true>(ctx, P, st) : launch_tc<1, false, true>(ctx, P, st);
+  }
+  if (range_on) return kpair == 2 ? launch_tc<2, false, true>(ctx, P, st) : launch_tc<1, false, true>(ctx, P, st);
   return kpair == 2 ? launch_tc<2, false, false>(ctx, P, st) : launch_tc<1, false, false>(ctx, P, st);
 }

@@ -14,6 +14,7 @@
 #define NM_POS_PE 63          // 3 + 3*2*10  (models/vanilla.py:60-79)
 #define NM_DIR_PE 27          // 3 + 3*2*4
 #define NM_VIEWS_HID 128      // width/2     (models/vanilla.py:112)
+#define NM_RANGE_FLAG_WORD 32  // word of ctx->d_counter the tensor-core kernels OR their range flag into
 
 // ---- packed network ------------------------------------------------------------------------
 // fp32 transposed weights ([in_padded][out]) for the SIMT kernel and fp16 UMMA-tiled weights for
@@ -30,7 +31,9 @@ struct NmNet {
   // tensor-core layout (see mlp_tc.cu for the tile format)
   __half* f16 = nullptr;
   size_t f16_halfs = 0;
-  float* tc_bias = nullptr;         // concatenated fp32 biases + alpha weights for the epilogues
+  float* tc_bias = nullptr;         // epilogue constants: 10 bias rows, alpha weights, output biases (mlp_tc.cu TcParams::consts)
+  float* consts_host = nullptr;     // pinned host copy (kernel parameters of the inference launches), refreshed lazily
+  bool consts_host_valid = false;
   __half* f16_bwd = nullptr;        // transposed slabs for the backward chain (mlp_tc_bwd.cu), packed on first use
   float* bw_wrgb = nullptr;         // rgb_linear.weight as [3][128] for the backward kernel's constant bank
   bool bwd_packed = false;
@@ -53,6 +56,12 @@ struct NmMesh {
   float cell = 0.f;
   int3 dims = {0, 0, 0};
   size_t cap_refs = 0, cap_cells = 0, cap_verts = 0, cap_faces = 0, cap_T = 0;
+  // near/far culling (rays.cu): vertices in Morton order, 32 per group, one bounding sphere per group
+  float4* vsorted = nullptr;      // [n_vgroups * 32] (x, y, z, 0); the tail of the last group repeats its first vertex
+  float4* vgroup = nullptr;       // [n_vgroups] centre + radius
+  int32_t n_vgroups = 0;
+  float4 vbound = {0, 0, 0, 0};   // bounding sphere of all vertices (whole-block early out)
+  size_t cap_vsorted = 0, cap_vgroup = 0;
   // signed-distance support (warp.cu): angle-weighted vertex pseudo-normals, face across each edge; built on first use
   bool has_T = false, pn_valid = false;
   double* vnorm = nullptr;        // [V,3]
@@ -149,6 +158,14 @@ __host__ __device__ __forceinline__ float nm_linspace01(int i, int steps) {
 // ---- implemented in the individual .cu files ------------------------------------------------
 int nm_impl_workspace(nm_ctx* ctx, size_t bytes, char** out);
 
+// rays.cu: vertex groups of a mesh for the near/far cull (called by nm_mesh_set with the host copy of the vertices), and
+// geometry_guided_near_far against a set mesh
+int nm_impl_build_vgroups(nm_ctx* ctx, NmMesh& m, const float* host_verts, const float* lo, const float* hi, cudaStream_t st);
+int nm_impl_near_far_mesh(nm_ctx* ctx, const NmMesh& m, const float* origins, const float* dirs, int64_t R, float geo_threshold,
+                          float* near_out, float* far_out, cudaStream_t st);
+// rays.cu: nm_raygen with an optional list of row-major pixel indices
+int nm_impl_raygen(nm_ctx* ctx, const nm_camera* cam, int mode, int64_t pix0, int64_t n, const int32_t* xy,
+                   const int32_t* pixels, float* origins, float* dirs, cudaStream_t stream);
 // composite.cu: raw2outputs whose last sample is followed by zero-density samples starting at z_end
 int nm_impl_raw2outputs_zend(nm_ctx* ctx, const float* raw, const float* z, const float* rays_d, int64_t R, int32_t S,
                              int32_t white_bkg, float z_end, float* rgb, float* depth, cudaStream_t st);
@@ -173,7 +190,7 @@ int nm_impl_dw_gemm(nm_ctx* ctx, const __half* g_pre, const __half* g_f, const _
 int nm_impl_colsum_f16(nm_ctx* ctx, const __half* src, int planes, int64_t n, int width, float* out, cudaStream_t st);
 int nm_tc_backward(nm_ctx* ctx, NmNet& net, const float* d_raw, const float* scale, int64_t n, const __half* st_v,
                    const uint32_t* st_m, __half* g_pre, __half* g_f, __half* g_v, cudaStream_t st);
-int nm_tc_forward(nm_ctx* ctx, const NmNet& net, const float* pts, const float* views,
+int nm_tc_forward(nm_ctx* ctx, NmNet& net, const float* pts, const float* views,
                   const float* origins, const float* dirs, const float* z, int64_t n,
                   int32_t group, float* raw, cudaStream_t st, const NmTrainStash* stash = nullptr);
 bool nm_tc_available();

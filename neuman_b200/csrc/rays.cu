@@ -16,7 +16,7 @@ struct RaygenParams {
   long long pix0, n;
 };
 
-__global__ void __launch_bounds__(256) k_raygen(RaygenParams p, const int32_t* __restrict__ xy,
+__global__ void __launch_bounds__(256) k_raygen(RaygenParams p, const int32_t* __restrict__ xy, const int32_t* __restrict__ pixels,
                                                  float* __restrict__ origins, float* __restrict__ dirs) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n) return;
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) k_raygen(RaygenParams p, const int32_t* _
     x = (double)xy[2 * i];
     y = (double)xy[2 * i + 1];
   } else {
-    long long pix = p.pix0 + i;
+    long long pix = pixels ? (long long)pixels[i] : p.pix0 + i;
     y = (double)(pix / p.W);      // row-major, y outer (render_utils.py:185)
     x = (double)(pix % p.W);
   }
@@ -68,6 +68,12 @@ static void invert3x3(const double* m, double* o) {
 extern "C" int nm_raygen(nm_ctx* ctx, const nm_camera* cam, int mode, int64_t pix0, int64_t n,
                          const int32_t* xy, float* origins, float* dirs, void* stream) {
   NM_ENTER(ctx);
+  return nm_impl_raygen(ctx, cam, mode, pix0, n, xy, nullptr, origins, dirs, (cudaStream_t)stream);
+}
+
+// pixels != NULL: the n rays are the row-major pixel indices pixels[0..n) (the frame drivers' pixel lists)
+int nm_impl_raygen(nm_ctx* ctx, const nm_camera* cam, int mode, int64_t pix0, int64_t n, const int32_t* xy,
+                   const int32_t* pixels, float* origins, float* dirs, cudaStream_t stream) {
   if (n == 0) return NM_OK;
   if (!cam || !origins || !dirs || n < 0 || (mode != 0 && mode != 1))
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_raygen: bad argument");
@@ -75,10 +81,10 @@ extern "C" int nm_raygen(nm_ctx* ctx, const nm_camera* cam, int mode, int64_t pi
   invert3x3(cam->K, p.Kinv);
   for (int i = 0; i < 16; ++i) p.c2w[i] = cam->c2w[i];
   p.W = cam->W; p.mode = mode; p.pix0 = pix0; p.n = n;
-  if (!xy && (pix0 < 0 || pix0 + n > (int64_t)cam->H * cam->W))
+  if (!xy && !pixels && (pix0 < 0 || pix0 + n > (int64_t)cam->H * cam->W))
     NM_FAIL(ctx, NM_ERR_INVALID, "nm_raygen: pixel range outside the image");
   unsigned blocks = (unsigned)((n + 255) / 256);
-  k_raygen<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, xy, origins, dirs);
+  k_raygen<<<blocks, 256, 0, stream>>>(p, xy, pixels, origins, dirs);
   NM_CHECK_LAUNCH(ctx);
   return NM_OK;
 }
@@ -199,6 +205,157 @@ extern "C" int nm_near_far(nm_ctx* ctx, const float* origins, const float* dirs,
   NM_CHECK_LAUNCH(ctx);
   k_near_far<<<blocks, 256, 0, (cudaStream_t)stream>>>(origins, dirs, R, verts, n_verts, thr2, geo_threshold, bounds,
                                                          near_out, far_out);
+  NM_CHECK_LAUNCH(ctx);
+  return NM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// near/far against a SET mesh (the frame drivers): the vertices are kept in Morton order in groups of 32 with one bounding
+// sphere per group; a ray tests the 32 vertex spheres of a group only when its line passes within radius + threshold of
+// the group's centre (conservative by 1 %: a culled vertex cannot yield a real root, so the result is exactly the
+// exhaustive loop's -- min / max do not depend on the order).  SMPL: 6890 vertices = 216 groups, of which a ray meets a
+// handful, instead of 6890 sphere tests per ray.
+#define VG_SIZE 32
+#define VG_TILE 64                   // groups per shared-memory tile (2048 vertices, 32 KB)
+#include <algorithm>
+#include <vector>
+
+static inline uint32_t expand10(uint32_t v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+
+int nm_impl_build_vgroups(nm_ctx* ctx, NmMesh& m, const float* hv, const float* lo, const float* hi, cudaStream_t st) {
+  const int nv = m.n_verts;
+  const int ng = (nv + VG_SIZE - 1) / VG_SIZE;
+  std::vector<std::pair<uint32_t, int>> key(nv);
+  float inv[3];
+  for (int c = 0; c < 3; ++c) inv[c] = 1023.f / fmaxf(hi[c] - lo[c], 1e-20f);
+  for (int v = 0; v < nv; ++v) {
+    uint32_t q[3];
+    for (int c = 0; c < 3; ++c) q[c] = (uint32_t)fminf(fmaxf((hv[3 * v + c] - lo[c]) * inv[c], 0.f), 1023.f);
+    key[v] = {(expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]), v};
+  }
+  std::sort(key.begin(), key.end());
+  std::vector<float4> sorted((size_t)ng * VG_SIZE), sph(ng);
+  for (int g = 0; g < ng; ++g) {
+    float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const int first = key[g * VG_SIZE].second;
+    for (int k = 0; k < VG_SIZE; ++k) {
+      const int i = g * VG_SIZE + k;
+      const int v = i < nv ? key[i].second : first;          // padding repeats a vertex of the group: no new roots
+      sorted[i] = make_float4(hv[3 * v], hv[3 * v + 1], hv[3 * v + 2], 0.f);
+      for (int c = 0; c < 3; ++c) { blo[c] = fminf(blo[c], hv[3 * v + c]); bhi[c] = fmaxf(bhi[c], hv[3 * v + c]); }
+    }
+    const float cx = 0.5f * (blo[0] + bhi[0]), cy = 0.5f * (blo[1] + bhi[1]), cz = 0.5f * (blo[2] + bhi[2]);
+    float r2 = 0.f;
+    for (int k = 0; k < VG_SIZE; ++k) {
+      const float4 p = sorted[g * VG_SIZE + k];
+      r2 = fmaxf(r2, (p.x - cx) * (p.x - cx) + (p.y - cy) * (p.y - cy) + (p.z - cz) * (p.z - cz));
+    }
+    sph[g] = make_float4(cx, cy, cz, sqrtf(r2));
+  }
+  if (m.cap_vsorted < sorted.size()) {
+    if (m.vsorted) { NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st)); NM_CHECK_CUDA(ctx, cudaFree(m.vsorted)); m.vsorted = nullptr; }
+    NM_CHECK_CUDA(ctx, cudaMalloc(&m.vsorted, sorted.size() * sizeof(float4)));
+    m.cap_vsorted = sorted.size();
+  }
+  if (m.cap_vgroup < (size_t)ng) {
+    if (m.vgroup) { NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st)); NM_CHECK_CUDA(ctx, cudaFree(m.vgroup)); m.vgroup = nullptr; }
+    NM_CHECK_CUDA(ctx, cudaMalloc(&m.vgroup, (size_t)ng * sizeof(float4)));
+    m.cap_vgroup = ng;
+  }
+  // pageable sources: the copies are complete (staged) when the calls return, so the vectors may go out of scope
+  NM_CHECK_CUDA(ctx, cudaMemcpyAsync(m.vsorted, sorted.data(), sorted.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+  NM_CHECK_CUDA(ctx, cudaMemcpyAsync(m.vgroup, sph.data(), (size_t)ng * sizeof(float4), cudaMemcpyHostToDevice, st));
+  m.n_vgroups = ng;
+  {
+    const float cx = 0.5f * (lo[0] + hi[0]), cy = 0.5f * (lo[1] + hi[1]), cz = 0.5f * (lo[2] + hi[2]);
+    float r2 = 0.f;
+    for (int v = 0; v < nv; ++v)
+      r2 = fmaxf(r2, (hv[3 * v] - cx) * (hv[3 * v] - cx) + (hv[3 * v + 1] - cy) * (hv[3 * v + 1] - cy) + (hv[3 * v + 2] - cz) * (hv[3 * v + 2] - cz));
+    m.vbound = make_float4(cx, cy, cz, sqrtf(r2));
+  }
+  return NM_OK;
+}
+
+__global__ void __launch_bounds__(256) k_near_far_groups(const float* __restrict__ origins, const float* __restrict__ dirs,
+                                                          long long R, const float4* __restrict__ vsorted,
+                                                          const float4* __restrict__ vgroup, int ng, float4 bound, float thr2,
+                                                          float thr, float* __restrict__ near_out, float* __restrict__ far_out) {
+  __shared__ float4 sv[VG_TILE * VG_SIZE];
+  __shared__ float4 sg[VG_TILE];
+  const int sl = threadIdx.x & (NF_LANES - 1);
+  long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / NF_LANES;
+  const bool live = r < R;
+  float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 1;
+  if (live) {
+    ox = origins[3 * r]; oy = origins[3 * r + 1]; oz = origins[3 * r + 2];
+    dx = dirs[3 * r]; dy = dirs[3 * r + 1]; dz = dirs[3 * r + 2];
+  }
+  const float dn2 = dx * dx + dy * dy + dz * dz;
+  // the reference's discriminant equals the geometric one only for unit directions: no cull otherwise
+  const bool unit = fabsf(dn2 - 1.f) <= 1e-3f;
+  float nr = INFINITY, fr = -INFINITY;
+  {
+    // whole-body cull: a block whose rays all pass clear of the mesh's bounding sphere (+ threshold) is done
+    const float cx = bound.x - ox, cy = bound.y - oy, cz = bound.z - oz;
+    const float t = cx * dx + cy * dy + cz * dz;
+    const float perp2 = (cx * cx + cy * cy + cz * cz) - t * t / dn2;
+    const float lim = (bound.w + thr) * 1.01f + 1e-5f;
+    const bool may_hit = live && (!unit || !(perp2 > lim * lim));
+    if (!__syncthreads_or(may_hit)) {
+      if (live && sl == 0) { near_out[r] = nr; far_out[r] = fr; }
+      return;
+    }
+  }
+  for (int g0 = 0; g0 < ng; g0 += VG_TILE) {
+    const int cnt = min(VG_TILE, ng - g0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt * VG_SIZE; j += blockDim.x) sv[j] = vsorted[(size_t)g0 * VG_SIZE + j];
+    if (threadIdx.x < cnt) sg[threadIdx.x] = vgroup[g0 + threadIdx.x];
+    __syncthreads();
+    if (live)
+      for (int g = sl; g < cnt; g += NF_LANES) {
+        const float4 b = sg[g];
+        const float cx = b.x - ox, cy = b.y - oy, cz = b.z - oz;
+        const float t = cx * dx + cy * dy + cz * dz;
+        const float perp2 = (cx * cx + cy * cy + cz * cz) - t * t / dn2;
+        const float lim = (b.w + thr) * 1.01f + 1e-5f;
+        if (unit && perp2 > lim * lim) continue;
+#pragma unroll 8
+        for (int k = 0; k < VG_SIZE; ++k) {
+          const float4 v = sv[g * VG_SIZE + k];
+          float ax = v.x - ox, ay = v.y - oy, az = v.z - oz;          // orig_v (ray_utils.py:211)
+          float z0 = ax * dx + ay * dy + az * dz;                      // einsum (:212)
+          float nrm = sqrtf(ax * ax + ay * ay + az * az);              // torch.norm (:213)
+          float disc = thr2 - (nrm * nrm - z0 * z0);
+          if (disc >= 0.f) {                                           // sqrt of a negative -> NaN -> skipped
+            float dzv = sqrtf(disc);
+            nr = fminf(nr, z0 - dzv);
+            fr = fmaxf(fr, z0 + dzv);
+          }
+        }
+      }
+  }
+#pragma unroll
+  for (int o = 1; o < NF_LANES; o <<= 1) {
+    nr = fminf(nr, __shfl_xor_sync(0xffffffffu, nr, o));
+    fr = fmaxf(fr, __shfl_xor_sync(0xffffffffu, fr, o));
+  }
+  if (live && sl == 0) { near_out[r] = nr; far_out[r] = fr; }
+}
+
+int nm_impl_near_far_mesh(nm_ctx* ctx, const NmMesh& m, const float* origins, const float* dirs, int64_t R, float geo_threshold,
+                          float* near_out, float* far_out, cudaStream_t st) {
+  if (R == 0) return NM_OK;
+  if (!m.vsorted || m.n_vgroups <= 0) return nm_near_far(ctx, origins, dirs, R, m.verts, m.n_verts, geo_threshold, near_out, far_out, st);
+  float thr2 = (float)((double)geo_threshold * (double)geo_threshold);
+  unsigned blocks = (unsigned)((R * NF_LANES + 255) / 256);
+  k_near_far_groups<<<blocks, 256, 0, st>>>(origins, dirs, R, m.vsorted, m.vgroup, m.n_vgroups, m.vbound, thr2, geo_threshold, near_out, far_out);
   NM_CHECK_LAUNCH(ctx);
   return NM_OK;
 }

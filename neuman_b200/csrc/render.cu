@@ -103,8 +103,9 @@ __global__ void k_fill(float* __restrict__ p, long long n, float v) {
     if (_rc != NM_OK) return _rc; \
   } while (0)
 
-int check_common(nm_ctx* ctx, const nm_camera* cam, const nm_render_opts* opt, int64_t pix0, int64_t n, const char* who) {
-  if (!cam || !opt || n < 0 || pix0 < 0 || pix0 + n > (int64_t)cam->H * cam->W)
+int check_common(nm_ctx* ctx, const nm_camera* cam, const nm_render_opts* opt, int64_t pix0, int64_t n, const int32_t* pixels,
+                 const char* who) {
+  if (!cam || !opt || n < 0 || (!pixels && (pix0 < 0 || pix0 + n > (int64_t)cam->H * cam->W)))
     NM_FAIL(ctx, NM_ERR_INVALID, std::string(who) + ": bad camera/options/pixel range");
   if (opt->samples_per_ray <= 0 || opt->importance_samples_per_ray < 0)
     NM_FAIL(ctx, NM_ERR_INVALID, std::string(who) + ": bad sample counts");
@@ -147,10 +148,10 @@ int copy_out(nm_ctx* ctx, float* dst, const float* src, size_t n, int host_out, 
 
 // ---------------------------------------------------------------------------------------------
 extern "C" int nm_render_vanilla(nm_ctx* ctx, int coarse_slot, int fine_slot, const nm_camera* cam,
-                                 const nm_render_opts* opt, int64_t pix0, int64_t n, float* rgb, float* depth,
-                                 int32_t host_out, void* stream) {
+                                 const nm_render_opts* opt, int64_t pix0, int64_t n, const int32_t* pixels, float* rgb,
+                                 float* depth, int32_t host_out, void* stream) {
   NM_ENTER(ctx);
-  TRY(check_common(ctx, cam, opt, pix0, n, "nm_render_vanilla"));
+  TRY(check_common(ctx, cam, opt, pix0, n, pixels, "nm_render_vanilla"));
   if (!slot_ok(ctx, coarse_slot) || (fine_slot >= 0 && !slot_ok(ctx, fine_slot)))
     NM_FAIL(ctx, NM_ERR_STATE, "nm_render_vanilla: net slot not packed");
   if (!rgb) NM_FAIL(ctx, NM_ERR_INVALID, "nm_render_vanilla: null rgb");
@@ -168,7 +169,7 @@ extern "C" int nm_render_vanilla(nm_ctx* ctx, int coarse_slot, int fine_slot, co
   if (A.off > ctx->ws_bytes) NM_FAIL(ctx, NM_ERR_STATE, "render: workspace arena overflow (internal sizing bug)");
   for (int64_t i = 0; i < n; i += C) {
     int64_t c = std::min<int64_t>(C, n - i);
-    TRY(nm_raygen(ctx, cam, 1, pix0 + i, c, nullptr, o, d, st));                       // shot_all_rays (:122)
+    TRY(nm_impl_raygen(ctx, cam, 1, pix0 + i, c, nullptr, pixels ? pixels + i : nullptr, o, d, st));                       // shot_all_rays (:122)
     float *raw, *z; int St;
     TRY(bkg_pass(ctx, coarse_slot, fine_slot, opt, o, d, c, z_c, raw_c, w_c, z_f, raw_f, &raw, &z, &St, st));
     float* rgb_dst = host_out ? rgb_s : rgb + 3 * i;
@@ -214,10 +215,10 @@ static int compact(nm_ctx* ctx, const float* near_v, const float* far_v, int64_t
 }
 
 extern "C" int nm_render_smpl_nerf(nm_ctx* ctx, int human_slot, int actor, const nm_camera* cam,
-                                   const nm_render_opts* opt, int64_t pix0, int64_t n, float* rgb, float* depth,
-                                   float* acc, int32_t host_out, void* stream) {
+                                   const nm_render_opts* opt, int64_t pix0, int64_t n, const int32_t* pixels, float* rgb,
+                                   float* depth, float* acc, int32_t host_out, void* stream) {
   NM_ENTER(ctx);
-  TRY(check_common(ctx, cam, opt, pix0, n, "nm_render_smpl_nerf"));
+  TRY(check_common(ctx, cam, opt, pix0, n, pixels, "nm_render_smpl_nerf"));
   if (!slot_ok(ctx, human_slot)) NM_FAIL(ctx, NM_ERR_STATE, "nm_render_smpl_nerf: net slot not packed");
   if (actor < 0 || actor >= NM_MAX_ACTORS || !ctx->meshes[actor].set)
     NM_FAIL(ctx, NM_ERR_STATE, "nm_render_smpl_nerf: mesh not set");
@@ -241,8 +242,8 @@ extern "C" int nm_render_smpl_nerf(nm_ctx* ctx, int human_slot, int actor, const
   if (A.off > ctx->ws_bytes) NM_FAIL(ctx, NM_ERR_STATE, "render: workspace arena overflow (internal sizing bug)");
   for (int64_t i = 0; i < n; i += C) {
     int64_t c = std::min<int64_t>(C, n - i);
-    TRY(nm_raygen(ctx, cam, 0, pix0 + i, c, nullptr, o, d, st));                        // shot_rays (:186)
-    TRY(nm_near_far(ctx, o, d, c, mesh.verts, mesh.n_verts, opt->geo_threshold, nr, fr, st));   // (:198)
+    TRY(nm_impl_raygen(ctx, cam, 0, pix0 + i, c, nullptr, pixels ? pixels + i : nullptr, o, d, st));                        // shot_rays (:186)
+    TRY(nm_impl_near_far_mesh(ctx, mesh, o, d, c, opt->geo_threshold, nr, fr, st));   // (:198)
     int64_t Rh = 0;
     TRY(compact(ctx, nr, fr, c, hit, &Rh, st));
     ctx->last_hit_rays += Rh;
@@ -274,10 +275,10 @@ extern "C" int nm_render_smpl_nerf(nm_ctx* ctx, int human_slot, int actor, const
 // ---------------------------------------------------------------------------------------------
 extern "C" int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int32_t n_actors,
                                 const int32_t* human_slots, const int32_t* actors, int32_t multi_person,
-                                const nm_camera* cam, const nm_render_opts* opt, int64_t pix0, int64_t n, float* rgb,
-                                float* depth, float* acc, int32_t host_out, void* stream) {
+                                const nm_camera* cam, const nm_render_opts* opt, int64_t pix0, int64_t n,
+                                const int32_t* pixels, float* rgb, float* depth, float* acc, int32_t host_out, void* stream) {
   NM_ENTER(ctx);
-  TRY(check_common(ctx, cam, opt, pix0, n, "nm_render_hybrid"));
+  TRY(check_common(ctx, cam, opt, pix0, n, pixels, "nm_render_hybrid"));
   if (!slot_ok(ctx, coarse_slot) || (fine_slot >= 0 && !slot_ok(ctx, fine_slot)))
     NM_FAIL(ctx, NM_ERR_STATE, "nm_render_hybrid: bkg net slot not packed");
   if (n_actors < 1 || n_actors > NM_MAX_ACTORS || !human_slots || !actors || (!multi_person && n_actors != 1))
@@ -324,7 +325,7 @@ extern "C" int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int
   if (A.off > ctx->ws_bytes) NM_FAIL(ctx, NM_ERR_STATE, "render: workspace arena overflow (internal sizing bug)");
   for (int64_t i = 0; i < n; i += C) {
     int64_t c = std::min<int64_t>(C, n - i);
-    TRY(nm_raygen(ctx, cam, 0, pix0 + i, c, nullptr, o, d, st));                        // shot_rays (:271 / :386)
+    TRY(nm_impl_raygen(ctx, cam, 0, pix0 + i, c, nullptr, pixels ? pixels + i : nullptr, o, d, st));                        // shot_rays (:271 / :386)
     float *raw_b, *z_b; int St;
     TRY(bkg_pass(ctx, coarse_slot, fine_slot, opt, o, d, c, z_c, raw_c, w_c, z_f, raw_f, &raw_b, &z_b, &St, st));
     float* rgb_dst = host_out ? rgb_s : rgb + 3 * i;
@@ -335,7 +336,7 @@ extern "C" int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int
       // all rays first get the background-only composite (miss rays keep it, :301-311)
       TRY(nm_raw2outputs(ctx, raw_b, z_b, d, c, St, nullptr, 1.f, opt->white_bkg, rgb_dst, nullptr, nullptr, nullptr, dep_dst, st));
       LAUNCH1D(k_fill, c, st, acc_dst, c, 0.f);
-      TRY(nm_near_far(ctx, o, d, c, mesh.verts, mesh.n_verts, opt->geo_threshold, nr, fr, st));   // (:299)
+      TRY(nm_impl_near_far_mesh(ctx, mesh, o, d, c, opt->geo_threshold, nr, fr, st));   // (:299)
       int64_t Rh = 0;
       TRY(compact(ctx, nr, fr, c, hit, &Rh, st));
       ctx->last_hit_rays += Rh;
@@ -366,7 +367,7 @@ extern "C" int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int
       for (int a = 0; a < n_actors; ++a) {
         const NmMesh& mesh = ctx->meshes[actors[a]];
         LAUNCH1D(k_fill_placeholder, c * S, st, z_a[a], (float4*)raw_a[a], c, S, opt->far_bkg * 2.f, opt->far_bkg * 3.f);
-        TRY(nm_near_far(ctx, o, d, c, mesh.verts, mesh.n_verts, opt->geo_threshold, nr, fr, st));   // (:415)
+        TRY(nm_impl_near_far_mesh(ctx, mesh, o, d, c, opt->geo_threshold, nr, fr, st));   // (:415)
         int64_t Rh = 0;
         TRY(compact(ctx, nr, fr, c, hit, &Rh, st));
         ctx->last_hit_rays += Rh;
@@ -406,5 +407,34 @@ extern "C" int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int
       NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
     }
   }
+  return NM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// frame reassembly after the gather of the ranks' pixel-list shards
+__global__ void k_assemble_frame(const float* __restrict__ shards, long long per, int planes, long long total,
+                                 const int32_t* __restrict__ pixels_all, float* __restrict__ rgb, float* __restrict__ depth,
+                                 float* __restrict__ acc) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long pix = pixels_all[i];
+  if (pix < 0) return;
+  const long long r = i / per, j = i - r * per;
+  const float* base = shards + r * planes * per;
+  rgb[3 * pix + 0] = base[3 * j + 0];
+  rgb[3 * pix + 1] = base[3 * j + 1];
+  rgb[3 * pix + 2] = base[3 * j + 2];
+  if (depth) depth[pix] = base[3 * per + j];
+  if (acc && planes > 4) acc[pix] = base[4 * per + j];
+}
+
+extern "C" int nm_assemble_frame(nm_ctx* ctx, const float* shards, int32_t world, int64_t per, int32_t planes,
+                                 const int32_t* pixels_all, float* rgb, float* depth, float* acc, void* stream) {
+  NM_ENTER(ctx);
+  if (!shards || !pixels_all || !rgb || world < 1 || per < 0 || (planes != 4 && planes != 5))
+    NM_FAIL(ctx, NM_ERR_INVALID, "nm_assemble_frame: bad argument");
+  const long long total = (long long)world * per;
+  cudaStream_t st = (cudaStream_t)stream;
+  LAUNCH1D(k_assemble_frame, total, st, shards, (long long)per, (int)planes, total, pixels_all, rgb, depth, acc);
   return NM_OK;
 }

@@ -4,6 +4,7 @@
 #include "nm_internal.cuh"
 
 #define TC_STEPS 11
+#define TC_CONST_FLOATS 272         // epilogue constants of the forward kernel (mlp_tc.cu: TcParams::consts)
 #define TC_KB_BYTES 16384          // one A k-block: 128 rows x 128 B
 #define TC_BIAS_STRIDE 256
 
@@ -119,6 +120,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
+}
+// K-major operand WITHOUT swizzle: core matrices of 8 rows x 16 bytes (rows contiguous), `lbo` bytes between the two core
+// matrices of a K = 16 step, `sbo` bytes between 8-row groups (0: every group reads the same core matrices)
+__device__ __forceinline__ uint64_t make_desc_ns(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
 }
 // UMMA instruction descriptor, kind::f16: D=f32 (bit4), A=B=f16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {

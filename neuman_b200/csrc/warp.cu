@@ -373,6 +373,7 @@ extern "C" int nm_mesh_set(nm_ctx* ctx, int actor, const float* verts, int32_t n
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int v = 0; v < n_verts; ++v)
     for (int c = 0; c < 3; ++c) { lo[c] = fminf(lo[c], hv[3 * v + c]); hi[c] = fmaxf(hi[c], hv[3 * v + c]); }
+  if ((rc = nm_impl_build_vgroups(ctx, m, hv.data(), lo, hi, st))) return rc;      // near/far cull structure (rays.cu)
   float3 bmin = make_float3(lo[0], lo[1], lo[2]);
   float3 binv = make_float3(1.f / fmaxf(hi[0] - lo[0], 1e-20f), 1.f / fmaxf(hi[1] - lo[1], 1e-20f), 1.f / fmaxf(hi[2] - lo[2], 1e-20f));
   size_t cub_bytes = 0;

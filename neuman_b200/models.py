@@ -104,24 +104,119 @@ def build_nerf(opt):
     return coarse, fine
 
 
-class HumanNeRF(nn.Module):
-    """models/human_nerf.py:20-90: container of the background coarse/fine nets and the canonical
-    human net (the offset nets are training-only, SURVEY.md §0.4, and not built here)."""
+class OffsetNet(nn.Module):
+    """models/vanilla.py:169-177: parameter container of one offset network (Embedder over (x, y, z, t) + an 8x256 NeRF trunk
+    with `output_linear` [3,256] and output scaling), so that `hybrid_model_state_dict` checkpoints load unchanged.  It is
+    a training-time network (trainers/human_nerf_trainer.py:241-278); the renderers never evaluate it and
+    no kernel is built for it: forward raises."""
 
-    def __init__(self, opt, poses=None, betas=None, alignments=None, scale=None):
+    def __init__(self, pos_pe, nerf):
+        super().__init__()
+        self.pos_pe, self.nerf = pos_pe, nerf
+
+    def forward(self, input_pts, cur_iter=None):
+        raise NotImplementedError("OffsetNet is training-only (trainers/human_nerf_trainer.py:241-278); its kernels are not built")
+
+
+def build_offset_net(opt):
+    """models/vanilla.py:180-205."""
+    st_pe = Embedder(opt.raw_pos_dim + 1, opt.pos_max_freq, opt.pos_N_freqs, opt.log_sampling, opt.include_input,
+                     min_freq=opt.pos_min_freq)
+    net = NeRF(depth=opt.nerf_depth, width=opt.nerf_width, input_ch=st_pe.out_dim, input_ch_views=0, output_ch=3,
+               use_viewdirs=False, scale=opt.offset_scale, scale_type=opt.offset_scale_type)
+    net = OffsetNet(st_pe, net)
+    return net.cuda() if opt.use_cuda else net
+
+
+class SMPL(nn.Module):
+    """Device mirror of the part of models/smpl.py:SMPL the path uses: `verts_transformations` (:109-162) and `forward`
+    (:164-215) on the CUDA LBS kernels (csrc/smpl.cu).  `model`: a path to an SMPL pickle (the reference's
+    data/smplx/smpl/SMPL_NEUTRAL.pkl layout: f, v_template, shapedirs, J_regressor, posedirs, kintree_table, weights)
+    or a dict with those keys (neuman_b200.synthetic.make_model())."""
+
+    def __init__(self, model, device="cuda"):
+        super().__init__()
+        if isinstance(model, str):
+            import pickle
+            with open(model, "rb") as fp:
+                model = pickle.load(fp, encoding="latin1")
+        dense = lambda a: np.asarray(a.todense() if hasattr(a, "todense") else a)
+        self.faces = np.asarray(model["f"]).astype(np.int64)
+        par = np.asarray(model["kintree_table"])[0].astype(np.int64)
+        self.device = torch.device(device)
+        self.dev_model = ops.SmplModelDevice(dense(model["v_template"]), dense(model["shapedirs"])[:, :, :10],
+                                             dense(model["J_regressor"]), dense(model["weights"]), par, device=self.device)
+
+    def verts_transformations(self, poses, betas, transl=None, return_tensor=True, concat_joints=False):
+        """-> (vertices [1,V(+J),3], T [1,V(+J),4,4]) float32 (numpy [V,3] / [V,4,4] when return_tensor=False)."""
+        verts, T = ops.smpl_verts_transformations(self.dev_model, poses, betas, concat_joints=concat_joints)
+        if transl is not None:
+            T = T.clone()
+            T[:, :3, 3] += torch.as_tensor(transl, dtype=torch.float32, device=T.device).reshape(1, 3)   # transl_4x4 @ L (:151-154)
+        if not return_tensor:
+            return verts.cpu().numpy(), T.cpu().numpy()
+        return verts[None], T[None]
+
+    def forward(self, poses, betas, transl=None, return_tensor=True, return_joints=False):
+        """SMPL.forward (:164-215): posed vertices = T . [v_shaped; 1] (pose blend shapes are not applied, :334)."""
+        verts, T = ops.smpl_verts_transformations(self.dev_model, poses, betas, concat_joints=True)
+        posed = torch.einsum("vij,vj->vi", T[:, :3, :3], verts) + T[:, :3, 3]
+        if transl is not None:
+            posed = posed + torch.as_tensor(transl, dtype=torch.float32, device=posed.device).reshape(1, 3)
+        nv = self.dev_model.n_verts
+        v, j = posed[:nv], posed[nv:]
+        if not return_tensor:
+            v, j = v.cpu().numpy(), j.cpu().numpy()
+        else:
+            v, j = v[None], j[None]
+        return (v, j) if return_joints else v
+
+
+class HumanNeRF(nn.Module):
+    """models/human_nerf.py:20-122: container of the background coarse/fine nets, the offset nets and the canonical human
+    net, plus -- when per-frame SMPL parameters are given -- `poses / betas / alignments / scale`, the `body_model`, the
+    'da' rest pose and `vertex_forward`.  `smpl_model`: path or dict for the body model (the reference hard-codes
+    <repo>/data/smplx/smpl/SMPL_NEUTRAL.pkl, which is licence-gated and absent here)."""
+
+    def __init__(self, opt, poses=None, betas=None, alignments=None, scale=None, smpl_model=None):
         super().__init__()
         self.coarse_bkg_net, self.fine_bkg_net = build_nerf(opt)
-        self.offset_nets = nn.ModuleList([])
+        self.offset_nets = nn.ModuleList([build_offset_net(opt) for _ in range(getattr(opt, "num_offset_nets", 0))])
         t = copy.deepcopy(opt)
         t.pos_min_freq = 0
         t.use_viewdirs = t.specular_can
         t.posenc = t.can_posenc
         self.coarse_human_net, _ = build_nerf(t)
+        self.body_model = None
         if poses is not None:
-            self.poses = nn.Parameter(torch.from_numpy(np.asarray(poses)).float())
-            self.betas = nn.Parameter(torch.from_numpy(np.asarray(betas)).float())
-            self.alignments = nn.Parameter(torch.from_numpy(np.asarray(alignments)).float())
+            assert betas is not None and alignments is not None and scale is not None
+            dev = "cuda" if opt.use_cuda else "cpu"
+            self.poses = nn.Parameter(torch.from_numpy(np.asarray(poses)).float().to(dev))
+            self.betas = nn.Parameter(torch.from_numpy(np.asarray(betas)).float().to(dev))
+            self.alignments = nn.Parameter(torch.from_numpy(np.asarray(alignments)).float().to(dev))
             self.scale = scale
+            da = torch.zeros(self.poses.shape[1] // 3, 3)
+            da[1, 2], da[2, 2] = 1.0, -1.0                                   # (:46-50)
+            self.da_smpl = nn.Parameter(da.reshape(1, -1).to(dev), requires_grad=False)
+            self.poses_orig, self.betas_orig = np.array(poses, copy=True), np.array(betas, copy=True)
+            if smpl_model is not None:
+                self.body_model = SMPL(smpl_model, device="cuda")
+
+    def vertex_forward(self, idx, pose=None, beta=None):
+        """models/human_nerf.py:92-122 -> (world_verts [1,V,3] f32, T_da2scene [1,V,4,4] f32) on the device: one
+        nm_smpl_scene_transforms call (LBS of the frame pose and of the 'da' pose, T_t2pose . inv(T_t2da), alignment^T and
+        the scene scale; float64 inside like data_io/neuman_helper.py:299-330, returned in the reference's float32).
+        Inference only: the SMPL / warp adjoints the human trainer differentiates through are not built."""
+        if self.body_model is None:
+            raise RuntimeError("HumanNeRF was built without an SMPL model (pass smpl_model=...)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in (self.poses, self.betas, self.alignments)):
+            raise NotImplementedError("vertex_forward under autograd (SMPL adjoint) is not built; wrap the call in torch.no_grad()")
+        pose = self.poses[idx][None] if pose is None else pose
+        beta = self.betas[idx][None] if beta is None else beta
+        m = self.body_model.dev_model
+        world, _, T = ops.smpl_scene_transforms(m, pose.detach(), beta.detach(), self.alignments[idx].detach().cpu().numpy(),
+                                                float(self.scale))
+        return world[None], T[:m.n_verts].float()[None]
 
 
 def default_opt(**over):
@@ -131,6 +226,6 @@ def default_opt(**over):
         use_cuda=torch.cuda.is_available(), nerf_depth=8, nerf_width=256, use_viewdirs=True, specular_can=True,
         raw_pos_dim=3, pos_min_freq=0, pos_max_freq=9, pos_N_freqs=10, raw_dir_dim=3, dir_max_freq=3, dir_N_freqs=4,
         log_sampling=True, include_input=True, can_posenc='rotate', rays_per_batch=2048, samples_per_ray=128,
-        white_bkg=True, importance_samples_per_ray=128, num_offset_nets=0)
+        white_bkg=True, importance_samples_per_ray=128, num_offset_nets=0, offset_scale=1.0, offset_scale_type='linear')
     o.__dict__.update(over)
     return o

@@ -9,15 +9,28 @@ the hot path (utils/ray_utils.py:53,55,70); the stub routes them to the float64 
 restatement in oracle/mesh_oracle.py ("parity unpinned" for that one stage -- libigl 2.2.1 itself
 is not available, environment.yml:13).
 
-/root/reference does not exist on the GPU box: nothing under tests -m gpu / bench.py / smoke() may
-import this file.
+/root/reference does not exist on the GPU box; there only the unmodified copy under baseline/_ref (git-ignored,
+tools/install_reference.py) can be imported, by bench.py's CPU arm and tests/test_gpu_dropin.py.
 """
 import importlib
 import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("NEUMAN_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """The reference tree: $NEUMAN_REFERENCE, else /root/reference (build container), else the unmodified copy that
+    tools/install_reference.py placed under baseline/_ref (it travels to the GPU box; used there by bench.py's CPU arm and
+    tests/test_gpu_dropin.py only)."""
+    for c in (os.environ.get("NEUMAN_REFERENCE"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")):
+        if c and os.path.isdir(os.path.join(c, "utils")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available():
@@ -47,6 +60,7 @@ def _stub(name, **attrs):
 
 
 def install_stubs():
+    import torch                        # noqa: F401  (torch inspects sys.modules while importing: load it before the stubs exist)
     from oracle import mesh_oracle
     if "igl" not in sys.modules or not hasattr(sys.modules["igl"], "_neuman_stub"):
         _stub("igl",

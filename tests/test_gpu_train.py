@@ -57,7 +57,7 @@ def test_dw_gemm(n):
     """k_dw_gemm (TMA-fed MN-major tcgen05 GEMMs, K = n) against fp32 matmuls of the same fp16 planes: fp32
     accumulation in a different order -> 1e-4 relative L2; rows 128.. of the views item stay zero."""
     from neuman_b200 import ops
-    from neuman_b200.ops import _p, _stream
+    from neuman_b200.ops import _p
     torch.manual_seed(n)
     g_pre = (torch.randn(8, n, 256, device=DEV) * 0.5).half()
     g_f = (torch.randn(n, 256, device=DEV) * 0.5).half()
@@ -67,7 +67,7 @@ def test_dw_gemm(n):
     ctx = ops._ctx_for(g_f)
     out = torch.full((9, 256, 256), float("nan"), device=DEV)
     bias = torch.full((9, 256), float("nan"), device=DEV)
-    ctx.check(ctx.lib.nm_dw_gemm(ctx.h, _p(g_pre), _p(g_f), _p(g_v), _p(sx), _p(sf), n, _p(out), _p(bias), _stream()))
+    ctx.check(ctx.lib.nm_dw_gemm(ctx.h, _p(g_pre), _p(g_f), _p(g_v), _p(sx), _p(sf), n, _p(out), _p(bias), ctx.stream()))
     ref = torch.zeros(9, 256, 256, device=DEV)
     for k in range(7):
         ref[k] = g_pre[k + 1].float().t() @ sx[k].float()

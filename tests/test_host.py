@@ -83,6 +83,70 @@ print('ok', rank)
     assert out.stdout.count("ok") == 2
 
 
+def test_tile_partition_covers_every_pixel_once():
+    """interleaved 16x16 tiles dealt round-robin; every pixel in exactly one shard, shards balanced to within
+    one tile, edge tiles clipped."""
+    from neuman_b200 import sharding
+    for (H, W) in ((720, 1280), (512, 512), (72, 100), (5, 7)):
+        for world in (1, 2, 3, 8):
+            seen = np.zeros(H * W, np.int32)
+            sizes = []
+            for r in range(world):
+                p = sharding.tile_pixels(H, W, r, world)
+                assert p.dtype == np.int32 and (p >= 0).all() and (p < H * W).all()
+                seen[p] += 1
+                sizes.append(p.size)
+            assert (seen == 1).all()
+            if (H, W) in ((720, 1280), (512, 512)) and world != 3:
+                assert max(sizes) == min(sizes)                          # BASELINE.json's frames split evenly over 1/2/4/8 GPUs
+            assert max(sizes) - min(sizes) <= 2 * sharding.TILE * sharding.TILE
+    # a tile is 16 consecutive pixels of 16 consecutive rows
+    p = sharding.tile_pixels(720, 1280, 3, 8)
+    assert p[0] == 3 * 16 and p[15] == 3 * 16 + 15 and p[16] == 1280 + 3 * 16
+
+
+def test_tile_shards_gather_world_size_2_gloo(tmp_path):
+    """Two gloo ranks fill their tile shards (CPU stand-in for the renderers), ONE all_gather of the equal-sized shards
+    moves them, and the pixel lists put every value back (the CPU restatement of nm_assemble_frame)."""
+    script = tmp_path / "w.py"
+    script.write_text(f"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {ROOT!r})
+from neuman_b200 import sharding
+dist.init_process_group('gloo')
+rank, world = dist.get_rank(), dist.get_world_size()
+H, W, planes = 72, 100, 5
+lists = [sharding.tile_pixels(H, W, r, world) for r in range(world)]
+per = max(x.size for x in lists)
+mine = torch.from_numpy(lists[rank]).long()
+shard = torch.zeros(planes * per)
+n = mine.numel()
+shard[:3 * per][:3 * n].view(n, 3)[:] = torch.stack([mine * 3.0, mine * 3.0 + 1, mine * 3.0 + 2], 1)      # fake rgb
+shard[3 * per:4 * per][:n] = mine + 0.25                                                                 # fake depth
+shard[4 * per:5 * per][:n] = mine + 0.5                                                                  # fake acc
+gathered = torch.empty(world * planes * per)
+dist.all_gather_into_tensor(gathered, shard)
+rgb, depth, acc = torch.full((H * W, 3), -1.0), torch.full((H * W,), -1.0), torch.full((H * W,), -1.0)
+for r in range(world):
+    base = gathered[r * planes * per:(r + 1) * planes * per]
+    idx = torch.from_numpy(lists[r]).long()
+    m = idx.numel()
+    rgb[idx] = base[:3 * per][:3 * m].view(m, 3)
+    depth[idx] = base[3 * per:4 * per][:m]
+    acc[idx] = base[4 * per:5 * per][:m]
+pix = torch.arange(H * W, dtype=torch.float32)
+assert torch.equal(rgb, torch.stack([pix * 3, pix * 3 + 1, pix * 3 + 2], 1)) and torch.equal(depth, pix + 0.25) and torch.equal(acc, pix + 0.5)
+dist.destroy_process_group()
+print('ok', rank)
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29534", str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2
+
+
 @pytest.mark.reference
 def test_install_rebinds_reference_modules():
     from oracle import ref_import

@@ -208,3 +208,24 @@ def test_render_human_and_hybrid_match(ref):
                                                [body["Ts"], body2["Ts"]], rays_per_batch=32, samples_per_ray=12,
                                                importance_samples_per_ray=8, geo_threshold=geo)
     assert np.allclose(r.reshape(H, W, 3), r_r, atol=2e-6) and np.allclose(d.reshape(H, W), d_r, atol=2e-6)
+
+
+def test_mirror_human_nerf_state_dict_matches_the_reference(ref):
+    """The host mirror (neuman_b200.models) creates the reference's parameters -- names, shapes, default-init values in the
+    same order -- including the offset nets, so `hybrid_model_state_dict` checkpoints load unchanged."""
+    import contextlib
+    import io
+    import neuman_b200 as nb
+    from oracle import ref_opts
+    opt = ref_opts.default_opt(num_offset_nets=2)
+    torch.manual_seed(11)
+    with contextlib.redirect_stdout(io.StringIO()):
+        r = ref.human_nerf.HumanNeRF(opt)
+    torch.manual_seed(11)
+    m = nb.HumanNeRF(nb.default_opt(use_cuda=False, num_offset_nets=2))
+    sr, sm = r.state_dict(), m.state_dict()
+    assert list(sr.keys()) == list(sm.keys())
+    for k in sr:
+        assert sr[k].shape == sm[k].shape and torch.equal(sr[k], sm[k]), k
+    assert any(k.startswith("offset_nets.1.nerf.output_linear") for k in sm)
+    m.load_state_dict(sr, strict=True)

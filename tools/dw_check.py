@@ -7,7 +7,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from neuman_b200 import ops                   # noqa: E402
-from neuman_b200.ops import _p, _stream       # noqa: E402
+from neuman_b200.ops import _p       # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
 torch.manual_seed(0)
@@ -21,7 +21,7 @@ sf = torch.randn(n, 256, device=dev).half()
 ctx = ops._ctx_for(g_f)
 out = torch.full((9, 256, 256), float("nan"), device=dev)
 bias = torch.full((9, 256), float("nan"), device=dev)
-ctx.check(ctx.lib.nm_dw_gemm(ctx.h, _p(g_pre), _p(g_f), _p(g_v), _p(sx), _p(sf), n, _p(out), _p(bias), _stream()))
+ctx.check(ctx.lib.nm_dw_gemm(ctx.h, _p(g_pre), _p(g_f), _p(g_v), _p(sx), _p(sf), n, _p(out), _p(bias), ctx.stream()))
 torch.cuda.synchronize()
 ref = torch.zeros(9, 256, 256, device=dev)
 for k in range(7):
@@ -41,7 +41,7 @@ if n >= 100000:
     for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ctx.check(ctx.lib.nm_dw_gemm(ctx.h, _p(g_pre), _p(g_f), _p(g_v), _p(sx), _p(sf), n, _p(out), _p(bias), _stream()))
+        ctx.check(ctx.lib.nm_dw_gemm(ctx.h, _p(g_pre), _p(g_f), _p(g_v), _p(sx), _p(sf), n, _p(out), _p(bias), ctx.stream()))
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
