@@ -32,20 +32,25 @@
 // Plan: which slabs a step consumes, where they live in the packed image.
 // ---------------------------------------------------------------------------------------------
 struct TcPlan {
-  uint32_t slab_off[TC_STEPS][6];   // byte offset inside one CTA-rank image
-  uint32_t slab_bytes[TC_STEPS];    // bytes per weight slab of this step (per CTA); its bias slab is a quarter of that
+  uint32_t slab_off[TC_STEPS][5];   // byte offset inside one CTA-rank image
+  uint32_t slab_bytes[TC_STEPS];    // bytes per slab of this step (per CTA)
   uint32_t image_bytes;             // size of one CTA-rank image
 };
 
-// Every layer's bias rides in the MMAs: each step 0..9 ends with one extra k-block, a "bias slab" [N rows][K = 16]
-// whose first two K columns hold the bias split into two fp16 values (hi + lo: 22 significand bits, fp32 accuracy after
-// the fp32 accumulation), multiplied by a constant A operand whose rows are all (1, 1, 0, ..., 0).  That operand is 256
-// bytes of shared memory: a K-major SWIZZLE_NONE descriptor with a zero stride between the 8-row groups makes all 128
-// rows read the same two core matrices.  The epilogue then has no bias loads and no adds at all -- they were its largest
-// cost (4 LDS.128 broadcasts + 16 FADD per 16 columns on the pipe that also feeds the UMMA operands and takes the
-// activation stores: profiles/r02_mlp_tc_experiments.md); one K = 16 MMA per step costs 1/16 of a layer's tensor time.
-__host__ __device__ constexpr int step_nkb(int s) { return s == 0 ? 2 : (s == 5 || s == 9) ? 6 : (s == 10 ? 2 : 5); }
-__host__ __device__ constexpr bool kb_is_bias(int s, int kb) { return s <= 9 && kb == step_nkb(s) - 1; }
+// Every layer's bias rides in the MMAs.  The last channel of each encoding is the constant 1 (channel 63 of the position
+// encoding, 27 of the direction encoding) and the weight column that multiplies it holds the bias (fp16, like every other
+// weight): steps 0, 5 and 9 read the PE block anyway, so there the bias costs nothing.  The K = 256 steps (1-4, 6-8) get
+// one extra k-block, a "bias slab" that is zero except for column 63, consumed by ONE K = 16 MMA against the last K slice
+// (channels 48..63) of whatever encoding the PE block holds at that moment: channels 48..62 meet zero weights, channel 63
+// is 1 in every position encoding, and the direction-encoding stores never touch that half of the block.  The epilogue
+// then has no bias loads and no adds at all -- they were its largest cost (4 LDS.128 broadcasts + 16 FADD per 16 columns
+// on the pipe that also feeds the UMMA operands and takes the activation stores: profiles/r02_mlp_tc_experiments.md); the
+// extra MMA costs 1/16 of a layer's tensor time.  (A variant with a 256-byte constant-ones A operand -- K-major without
+// swizzle, zero stride between row groups -- and a hi + lo bias pair in a 4 KB slab computed the right values but ran 10 %
+// slower and dead-locked in multi-round launches; with five slabs per step and a five-slot ring shared by both tiles there
+// is no room for a sixth slab at steps 5 and 9 either.  Not kept.)
+__host__ __device__ constexpr int step_nkb(int s) { return s == 0 ? 1 : (s == 10 ? 2 : 5); }
+__host__ __device__ constexpr bool kb_is_bias(int s, int kb) { return kb == 4 && s != 5 && s != 9 && s >= 1 && s <= 8; }
 __host__ __device__ constexpr int step_N(int s) { return s <= 8 ? 256 : (s == 9 ? 128 : 16); }
 // k-block kb of step s reads the PE buffer (else activation block `act_kb`)
 __host__ __device__ constexpr bool kb_is_pe(int s, int kb) { return (s == 0) || (s == 5 && kb == 0) || (s == 9 && kb == 4); }
@@ -67,9 +72,7 @@ struct TcCfg {
   static constexpr int OFF_TMEMPTR = OFF_BAR + 8 * N_BAR;
   // alpha-head partials of the upper column half, one float per row and tile in flight
   static constexpr int OFF_ALPHA = (OFF_TMEMPTR + 16 + 127) & ~127;
-  // constant A operand of the bias MMAs: two 8 x 16 B core matrices, every row = (1, 1, 0, 0, 0, 0, 0, 0 | 0 x 8) in fp16
-  static constexpr int OFF_ONES = OFF_ALPHA + NT * 512;
-  static constexpr int SMEM_USED = OFF_ONES + 256;
+  static constexpr int SMEM_USED = OFF_ALPHA + NT * 512;
   static constexpr int SMEM_SLACK = (232448 - SMEM_USED) < 1024 ? (232448 - SMEM_USED) : 1024;   // alignment slack that still fits 227 KB
   static constexpr int SMEM_BYTES = SMEM_USED + SMEM_SLACK;
 };
@@ -86,6 +89,14 @@ struct TcCfg {
 #define TC_CONST_OUT 256
 __constant__ __align__(16) float c_tc_consts[TC_CONST_FLOATS];
 
+// with two tiles sharing every slab, a step's slabs must all fit the ring at once (see step_nkb)
+__host__ __device__ constexpr bool ring_holds_a_step(int nslot) {
+  for (int s = 0; s < TC_STEPS; ++s)
+    if (step_nkb(s) > nslot) return false;
+  return true;
+}
+static_assert(ring_holds_a_step(TcCfg<2>::NSLOT), "a step has more slabs than the ring has slots: tiles A and B would deadlock");
+
 struct TcParams {
   const uint8_t* wimg;      // packed slabs, kPair images back to back
   TcPlan plan;
@@ -94,6 +105,7 @@ struct TcParams {
   float* raw;
   long long n_tiles;        // number of (pair-)tiles
   int32_t* range_flag;      // device word: bit 0 is set when an activation reached the fp16 range limit (saturated)
+  int range_phase;          // sampled range check (kRange == 1): the rounds r with r % 64 == range_phase % 64 are checked
   // training forward (kTrain): fp16 activation stash for the backward pass, planes of n rows each
   __half* st_x;             // [8][n][256] post-ReLU outputs of layers 0..7
   __half* st_f;             // [n][256]    feature_linear output
@@ -166,6 +178,7 @@ __device__ __forceinline__ void encode_f16(const NmPeSpec& pe, const float x[3],
       }
     }
   }
+  ch[nq == 30 ? 63 : 27] = 1.f;          // the constant channel that multiplies the bias column of the weight slabs
 #pragma unroll
   for (int i = 0; i < 32; ++i) out[i] = pack_f16x2(ch[2 * i], ch[2 * i + 1], false);
 }
@@ -276,7 +289,7 @@ __device__ __forceinline__ void epi_step(const TcParams& P, uint32_t t_lane, flo
     if (P.trace && blockIdx.x < 2 && (idx) < 256) P.trace[((blockIdx.x * 2 + (role)) * 4 + (ev)) * 256 + (idx)] = clock64(); \
   } while (0)
 
-template <int kPair, bool kTrain, bool kRange>
+template <int kPair, bool kTrain, int kRange>
 __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __grid_constant__ TcParams P) {
   using C = TcCfg<kPair>;
   constexpr int NT = C::NT, NSLOT = C::NSLOT;
@@ -316,11 +329,6 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
     tmem_alloc<kPair>(smem_u32(tmem_ptr_smem), 512);
     tmem_relinquish<kPair>();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 80) {           // 16 rows of 16 bytes: the first 8 carry the two ones
-    const int r = threadIdx.x - 64;
-    *reinterpret_cast<uint4*>(smem + C::OFF_ONES + 16 * r) = r < 8 ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-    fence_async_smem();
-  }
   tc_fence_before();
   __syncthreads();
   if (kPair == 2) cluster_sync_all();
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
       for (long long round = 0; round < n_rounds; ++round) {
         for (int s = 0; s < TC_STEPS; ++s) {
           for (int kb = 0; kb < step_nkb(s); ++kb, ++q) {
-            const uint32_t bytes = kb_is_bias(s, kb) ? P.plan.slab_bytes[s] / 4 : P.plan.slab_bytes[s];
+            const uint32_t bytes = P.plan.slab_bytes[s];
             const uint32_t slot = q % NSLOT, gen = q / NSLOT;
             mbar_wait(bar_empty(slot), (gen & 1) ^ 1);
             mbar_arrive_expect_tx(bar_full(slot), bytes);
@@ -385,19 +393,16 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
                 mbar_wait(bar_peready, (uint32_t)(pe_use(round, pe_k, t) & 1));
                 tc_fence_after();
               }
-              const uint32_t a_addr = is_pe ? sbase + C::OFF_PE
-                                            : sbase + C::OFF_ACT + (t * 4 + kb_act_index(s, kb)) * TC_KB_BYTES;
-              const uint64_t a_desc = make_desc(a_addr);
-              const uint64_t b_desc = make_desc(sbase + C::OFF_RING + slot * C::SLOT_BYTES);
+              // (descriptors are computed by the whole warp, outside the elected-lane region: they stay in uniform registers)
+              const uint32_t a_addr = (is_pe || is_bias) ? sbase + C::OFF_PE
+                                                         : sbase + C::OFF_ACT + (t * 4 + kb_act_index(s, kb)) * TC_KB_BYTES;
+              // K advances by 32 B (= 2 in descriptor address units) inside the 128-byte swizzle atom; a bias slab is one
+              // K = 16 MMA on the last K slice (channels 48..63 of the PE block x columns 48..63 of the slab)
+              const uint64_t a_desc = make_desc(a_addr) + (is_bias ? 6 : 0);
+              const uint64_t b_desc = make_desc(sbase + C::OFF_RING + slot * C::SLOT_BYTES) + (is_bias ? 6 : 0);
               if (issuer) {
-                if (is_bias) {
-                  // D += ones[128 x 16] . bias_slab[N x 16]^T: both operands K-major without swizzle (core matrices of
-                  // 8 rows x 16 B, 128 B apart along K); A: zero stride between row groups, B: 256 B between row groups
-                  umma_f16<kPair>(d_tmem, make_desc_ns(sbase + C::OFF_ONES, 128, 0),
-                                  make_desc_ns(sbase + C::OFF_RING + slot * C::SLOT_BYTES, 128, 256), idesc, 1);
-                } else {
-                  // K advances by 32 B (= 2 in descriptor address units) inside the 128-byte swizzle atom
-                  umma_f16<kPair>(d_tmem, a_desc, b_desc, idesc, kb != 0);
+                umma_f16<kPair>(d_tmem, a_desc, b_desc, idesc, kb != 0);
+                if (!is_bias) {
                   umma_f16<kPair>(d_tmem, a_desc + 2, b_desc + 2, idesc, 1);
                   if (kb_ksteps(s, kb) == 4) {
                     umma_f16<kPair>(d_tmem, a_desc + 4, b_desc + 4, idesc, 1);
@@ -509,6 +514,8 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
       float alpha[NT][4];
 #pragma unroll
       for (int t = 0; t < NT; ++t) alpha[t][0] = alpha[t][1] = alpha[t][2] = alpha[t][3] = 0.f;
+      const long long rperiod = n_rounds < 64 ? n_rounds : 64;
+      const bool track = kRange == 2 || (kRange == 1 && (round % rperiod) == (P.range_phase % rperiod));
       for (int s = 0; s < TC_STEPS; ++s, ++nstep) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
@@ -522,17 +529,25 @@ __global__ void __launch_bounds__(TcCfg<kPair>::THREADS, 1) k_mlp_tc(const __gri
             // step ago: it must have been read before the slice is overwritten (the other tile's store may still fly)
             if (kTrain) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
             uint4 signs = make_uint4(0, 0, 0, 0);
+            // range flag (kRange 0: off, 2: every sample, 1: every 64th round of the launch, the phase rotating from
+            // launch to launch -- the packed-half max costs ~4 % of the kernel when it runs on every sample)
+#define NM_EPI(RELU, ALPHA, CB, NC)                                                                         \
+  do {                                                                                                       \
+    if (track) epi_step<RELU, ALPHA, CB, NC, kParam, true>(P, t_lane, alpha[t], act, row, signs, rng);         \
+    else epi_step<RELU, ALPHA, CB, NC, kParam, false>(P, t_lane, alpha[t], act, row, signs, rng);              \
+  } while (0)
             if (g == 0) {
-              if (s == 7) epi_step<true, true, 0, 128, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
-              else if (s == 8) epi_step<false, false, 0, 128, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
-              else if (s == 9) epi_step<true, false, 0, 64, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
-              else epi_step<true, false, 0, 128, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
+              if (s == 7) NM_EPI(true, true, 0, 128);
+              else if (s == 8) NM_EPI(false, false, 0, 128);
+              else if (s == 9) NM_EPI(true, false, 0, 64);
+              else NM_EPI(true, false, 0, 128);
             } else {
-              if (s == 7) epi_step<true, true, 128, 128, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
-              else if (s == 8) epi_step<false, false, 128, 128, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
-              else if (s == 9) epi_step<true, false, 64, 64, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
-              else epi_step<true, false, 128, 128, kParam, kRange>(P, t_lane, alpha[t], act, row, signs, rng);
+              if (s == 7) NM_EPI(true, true, 128, 128);
+              else if (s == 8) NM_EPI(false, false, 128, 128);
+              else if (s == 9) NM_EPI(true, false, 64, 64);
+              else NM_EPI(true, false, 128, 128);
             }
+#undef NM_EPI
             if (kTrain && s < 8 && valid_of(round, t, row))
               reinterpret_cast<uint4*>(P.st_m + ((size_t)s * P.in.n + sample_of(round, t, row)) * 8)[g] = signs;
             if (kTrain && s == 9 && valid_of(round, t, row))   // views layer: 64 columns per thread -> words 2g, 2g+1 of plane 8
@@ -614,25 +629,25 @@ struct PackSrc {
 
 // weight of (step s, output n, k-block kb, kk in [0,64)) or 0 for padding
 __device__ __forceinline__ float src_weight(const PackSrc& S, int s, int n, int kb, int kk) {
-  if (s == 0) return kk < NM_POS_PE ? S.w[0][(size_t)n * NM_POS_PE + kk] : 0.f;
+  if (kb_is_bias(s, kb)) {                       // bias slab of a K = 256 step: only the column of PE channel 63 is non-zero
+    if (kk != 63) return 0.f;
+    return s == 8 ? S.feat_b[n] : S.b[s][n];
+  }
+  if (s == 0) return kk < NM_POS_PE ? S.w[0][(size_t)n * NM_POS_PE + kk] : S.b[0][n];           // kk == 63: bias
   if (s >= 1 && s <= 7 && s != 5) return S.w[s][(size_t)n * 256 + kb * 64 + kk];
   if (s == 5) {
     const int ld = NM_POS_PE + 256;
-    if (kb == 0) return kk < NM_POS_PE ? S.w[5][(size_t)n * ld + kk] : 0.f;
+    if (kb == 0) return kk < NM_POS_PE ? S.w[5][(size_t)n * ld + kk] : S.b[5][n];
     return S.w[5][(size_t)n * ld + NM_POS_PE + (kb - 1) * 64 + kk];
   }
   if (s == 8) return S.feat[(size_t)n * 256 + kb * 64 + kk];
   if (s == 9) {
     const int ld = 256 + NM_DIR_PE;
     if (kb < 4) return S.views[(size_t)n * ld + kb * 64 + kk];
-    return kk < NM_DIR_PE ? S.views[(size_t)n * ld + 256 + kk] : 0.f;
+    return kk < NM_DIR_PE ? S.views[(size_t)n * ld + 256 + kk] : (kk == NM_DIR_PE ? S.views_b[n] : 0.f);    // kk == 27: bias
   }
   // s == 10: rgb, N padded 3 -> 16 (its bias is added with the alpha bias when the output is written)
   return n < 3 ? S.rgb[(size_t)n * 128 + kb * 64 + kk] : 0.f;
-}
-
-__device__ __forceinline__ float src_bias(const PackSrc& S, int s, int n) {
-  return s <= 7 ? S.b[s][n] : (s == 8 ? S.feat_b[n] : S.views_b[n]);
 }
 
 __global__ void k_tc_pack(PackSrc S, TcPlan plan, int kpair, __half* __restrict__ out) {
@@ -648,15 +663,6 @@ __global__ void k_tc_pack(PackSrc S, TcPlan plan, int kpair, __half* __restrict_
       if (byte >= plan.slab_off[ss][k]) { s = ss; kb = k; }
   const uint32_t in_slab = byte - plan.slab_off[s][kb];
   const int n_cta = step_N(s) / kpair;
-  if (kb_is_bias(s, kb)) {
-    // K-major, no swizzle: [n / 8][k / 8][n % 8][k % 8] halves; k = 0: fp16(b), k = 1: fp16(b - fp16(b)), else 0
-    const int n_local = (in_slab >> 8) * 8 + ((in_slab & 127) >> 4);
-    const int kk = ((in_slab >> 7) & 1) * 8 + ((in_slab & 15) >> 1);
-    const float b = src_bias(S, s, rank * n_cta + n_local);
-    const __half hi = __float2half_rn(b);
-    out[(size_t)rank * (plan.image_bytes / 2) + e] = kk == 0 ? hi : (kk == 1 ? __float2half_rn(b - __half2float(hi)) : __float2half_rn(0.f));
-    return;
-  }
   const int n_local = in_slab >> 7;
   const int chunk_phys = (in_slab & 127) >> 4;
   const int chunk = chunk_phys ^ (n_local & 7);                         // undo the 128B swizzle
@@ -722,7 +728,7 @@ static TcPlan make_plan(int kpair) {
   uint32_t off = 0;
   for (int s = 0; s < TC_STEPS; ++s) {
     p.slab_bytes[s] = (uint32_t)(step_N(s) / kpair) * 128u;
-    for (int kb = 0; kb < step_nkb(s); ++kb) { p.slab_off[s][kb] = off; off += kb_is_bias(s, kb) ? p.slab_bytes[s] / 4 : p.slab_bytes[s]; }
+    for (int kb = 0; kb < step_nkb(s); ++kb) { p.slab_off[s][kb] = off; off += p.slab_bytes[s]; }
   }
   p.image_bytes = off;
   return p;
@@ -755,7 +761,7 @@ int nm_tc_pack(nm_ctx* ctx, NmNet& net, cudaStream_t st) {
   return NM_OK;
 }
 
-template <int kPair, bool kTrain, bool kRange>
+template <int kPair, bool kTrain, int kRange>
 static int launch_tc(nm_ctx* ctx, const TcParams& P, cudaStream_t st) {
   using C = TcCfg<kPair>;
   NM_SET_SMEM_ONCE(ctx, (k_mlp_tc<kPair, kTrain, kRange>), C::SMEM_BYTES);
@@ -795,6 +801,7 @@ int nm_tc_forward(nm_ctx* ctx, NmNet& net, const float* pts, const float* views,
   P.trace = nullptr;
   P.dbg = 0;
   P.range_flag = ctx->d_counter + NM_RANGE_FLAG_WORD;
+  P.range_phase = (int)(ctx->range_seq++ % 64);
   if (const char* e = getenv("NEUMAN_TC_DEBUG")) P.dbg = atoi(e);
   P.st_x = stash ? stash->x : nullptr; P.st_f = stash ? stash->f : nullptr; P.st_v = stash ? stash->v : nullptr;
   P.st_m = stash ? stash->m : nullptr;
@@ -817,11 +824,15 @@ int nm_tc_forward(nm_ctx* ctx, NmNet& net, const float* pts, const float* views,
     memcpy(P.consts, net.consts_host, sizeof(P.consts));
   }
   if (const char* e = getenv("NEUMAN_TC_TRACE")) P.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
-  static const bool range_on = !(getenv("NEUMAN_TC_RANGE") && getenv("NEUMAN_TC_RANGE")[0] == '0');
-  if (P.st_x) {
-    if (range_on) return kpair == 2 ? launch_tc<2, true, true>(ctx, P, st) : launch_tc<1, true, true>(ctx, P, st);
-    return kpair == 2 ? launch_tc<2, true, false>(ctx, P, st) : launch_tc<1, true, false>(ctx, P, st);
-  }
-  if (range_on) return kpair == 2 ? launch_tc<2, false, true>(ctx, P, st) : launch_tc<1, false, true>(ctx, P, st);
-  return kpair == 2 ? launch_tc<2, false, false>(ctx, P, st) : launch_tc<1, false, false>(ctx, P, st);
+  // NEUMAN_TC_RANGE: 0 = no range flag, 1 (default) = sampled (every 64th round, rotating phase), 2 = every sample
+  static const int range_mode = [] { const char* e = getenv("NEUMAN_TC_RANGE"); return e ? atoi(e) : 1; }();
+#define NM_LAUNCH(TRAIN)                                                                                                  \
+  do {                                                                                                                     \
+    if (range_mode <= 0) return kpair == 2 ? launch_tc<2, TRAIN, 0>(ctx, P, st) : launch_tc<1, TRAIN, 0>(ctx, P, st);       \
+    if (range_mode == 1) return kpair == 2 ? launch_tc<2, TRAIN, 1>(ctx, P, st) : launch_tc<1, TRAIN, 1>(ctx, P, st);       \
+    return kpair == 2 ? launch_tc<2, TRAIN, 2>(ctx, P, st) : launch_tc<1, TRAIN, 2>(ctx, P, st);                            \
+  } while (0)
+  if (P.st_x) NM_LAUNCH(true);
+  NM_LAUNCH(false);
+#undef NM_LAUNCH
 }

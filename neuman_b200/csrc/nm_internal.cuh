@@ -82,6 +82,7 @@ struct nm_ctx {
   size_t ws_bytes = 0;
   int64_t last_mlp_evals = 0;
   int64_t last_hit_rays = 0;
+  uint32_t range_seq = 0;         // launch counter of the tensor-core MLP (rotates the phase of its sampled range check)
   int32_t* d_counter = nullptr;   // small device scratch (compaction counters)
   int32_t* h_counter = nullptr;   // pinned host mirror
   double* can64 = nullptr;        // float64 canonical points scratch (warp.cu)

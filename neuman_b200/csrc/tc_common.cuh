@@ -28,7 +28,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
 // polling wait with a sleep between probes: for roles that run far ahead of their consumer (the bulk-TMA
-// producer, the relay), so that their spinning does not burn issue slots and power
+// producer, the relay, the encoding warps), so that their spinning does not burn issue slots and power
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns) {
   uint32_t done = 0;
   while (true) {
