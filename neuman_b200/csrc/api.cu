@@ -59,6 +59,7 @@ extern "C" int nm_ctx_destroy(nm_ctx* ctx) {
   for (auto& m : ctx->meshes) free_mesh(m);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->can64) cudaFree(ctx->can64);
+  if (ctx->face_tmp) cudaFree(ctx->face_tmp);
   for (auto e : ctx->prof_events) cudaEventDestroy(e);
   if (ctx->d_counter) cudaFree(ctx->d_counter);
   if (ctx->h_counter) cudaFreeHost(ctx->h_counter);

@@ -92,6 +92,8 @@ struct nm_ctx {
   size_t prof_used = 0;
   int64_t prof_evals = 0;
   size_t can64_cap = 0;
+  int32_t* face_tmp = nullptr;    // winning-face scratch of the warp stage (warp.cu)
+  size_t face_cap = 0;
 };
 
 // Every C entry point runs on the ctx's device whatever device the calling thread has current (a process may hold

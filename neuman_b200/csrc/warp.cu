@@ -238,18 +238,27 @@ __device__ __forceinline__ int bvh_nearest_face(const BvhView& B, V3<float> p, i
   return best_f;
 }
 
-__global__ void __launch_bounds__(128) k_warp_points(BvhView B, const float* __restrict__ verts,
-                                                      const int32_t* __restrict__ faces, const double* __restrict__ T,
-                                                      const float* __restrict__ pts, long long n,
-                                                      double* __restrict__ can64, float* __restrict__ closest_out,
-                                                      int32_t* __restrict__ face_out) {
+// The search and the float64 evaluation are two kernels: the traversal is a latency-bound pointer chase that wants many
+// resident warps (fp32, ~40 registers), the evaluation needs ~80 registers of float64 state.
+__global__ void __launch_bounds__(128) k_warp_nearest(BvhView B, const float* __restrict__ pts, long long n,
+                                                       int32_t* __restrict__ face_out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < n;
   const long long ii = live ? i : n - 1;
   V3<float> p{pts[3 * ii], pts[3 * ii + 1], pts[3 * ii + 2]};
   __shared__ int s_stack[4][64];
   const int best_f = bvh_nearest_face(B, p, s_stack[threadIdx.x >> 5]);
-  if (!live) return;
+  if (live) face_out[i] = best_f;
+}
+
+__global__ void __launch_bounds__(128) k_warp_points(const float* __restrict__ verts, const int32_t* __restrict__ faces,
+                                                      const double* __restrict__ T, const float* __restrict__ pts, long long n,
+                                                      const int32_t* __restrict__ face_in, double* __restrict__ can64,
+                                                      float* __restrict__ closest_out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  V3<float> p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+  const int best_f = face_in[i];
   // ---- float64 re-evaluation on the winning triangle (utils/ray_utils.py:53-58) ----
   int i0 = faces[3 * best_f], i1 = faces[3 * best_f + 1], i2 = faces[3 * best_f + 2];
   V3<double> P{(double)p.x, (double)p.y, (double)p.z};
@@ -275,7 +284,6 @@ __global__ void __launch_bounds__(128) k_warp_points(BvhView B, const float* __r
   double cz = Mi[8] * P.x + Mi[9] * P.y + Mi[10] * P.z + Mi[11];
   can64[3 * i] = cx; can64[3 * i + 1] = cy; can64[3 * i + 2] = cz;
   if (closest_out) { closest_out[3 * i] = (float)Q.x; closest_out[3 * i + 1] = (float)Q.y; closest_out[3 * i + 2] = (float)Q.z; }
-  if (face_out) face_out[i] = best_f;
 }
 
 // can_dirs: normalised forward difference along the ray, last one duplicated (:62-64), in float64
@@ -425,7 +433,20 @@ extern "C" int nm_warp_to_canonical(nm_ctx* ctx, int actor, const float* pts, in
   }
   double* can64 = ctx->can64;
   BvhView B = bvh_view(m);
-  k_warp_points<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, m.verts, m.faces, m.T, pts, n, can64, closest, face_id);
+  // winning faces: the caller's buffer, or the tail of the float64 scratch (3 doubles per point, the ints take a sixth)
+  int32_t* fid = face_id;
+  if (!fid) {
+    if ((size_t)n > ctx->face_cap) {
+      if (ctx->face_tmp) { NM_CHECK_CUDA(ctx, cudaDeviceSynchronize()); NM_CHECK_CUDA(ctx, cudaFree(ctx->face_tmp)); ctx->face_tmp = nullptr; }
+      size_t want = (size_t)n + ((size_t)n >> 3);
+      NM_CHECK_CUDA(ctx, cudaMalloc(&ctx->face_tmp, want * sizeof(int32_t)));
+      ctx->face_cap = want;
+    }
+    fid = ctx->face_tmp;
+  }
+  k_warp_nearest<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, pts, n, fid);
+  NM_CHECK_LAUNCH(ctx);
+  k_warp_points<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(m.verts, m.faces, m.T, pts, n, fid, can64, closest);
   NM_CHECK_LAUNCH(ctx);
   k_warp_dirs<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(can64, R, S, can_pts, can_dirs);
   NM_CHECK_LAUNCH(ctx);

@@ -13,6 +13,7 @@ from ._lib import Context, NmRenderOpts
 
 DEFAULT_GEO_THRESH = ops.DEFAULT_GEO_THRESH
 CHUNK = 32768            # device-side rays per chunk
+SMPL_CHUNK = 262144      # human-only renders: few rays hit, one hit-count read-back per chunk -> fewer, larger chunks (7 KB / ray)
 
 
 def _device_of(net):
@@ -123,7 +124,7 @@ def render_vanilla(coarse_net, cap, fine_net=None, rays_per_batch=32768, samples
 
 def render_smpl_nerf_range(net, cap, posed_verts, faces, Ts, samples_per_ray=64, white_bkg=True, render_can=False,
                            geo_threshold=DEFAULT_GEO_THRESH, interval_comp=1.0, pix0=0, n=None, host_out=True,
-                           chunk=CHUNK, pixels=None, out=None):
+                           chunk=SMPL_CHUNK, pixels=None, out=None):
     device = _device_of(net)
     ctx = _ctx(device)
     n, pix = _pixel_args(pixels, cap, pix0, n, device)

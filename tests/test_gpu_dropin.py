@@ -12,6 +12,7 @@ import torch
 
 import neuman_b200 as nb
 from neuman_b200._lib import Context
+from oracle import neuman_oracle as no
 from oracle import ref_import, ref_opts, scenes
 from tests import util
 
@@ -58,18 +59,22 @@ def test_reference_render_vanilla_runs_on_the_cuda_path(ref):
                      importance_samples_per_ray=40, return_depth=True)
     assert launches() > l0, "the reference's render_vanilla did not reach libneuman_b200"
     assert isinstance(rgb, np.ndarray) and rgb.dtype == np.float32 and rgb.shape == (20, 28, 3)
-    assert np.abs(rgb - f["van_rgb"]).max() < TOL and np.abs(dep - f["van_depth"]).max() < 3 * TOL
+    cp, fp = no.net_params_from_joiner(coarse), no.net_params_from_joiner(fine)
+    fl = util.floors16(lambda: no.render_vanilla(cp, fp, f["van_K"], f["van_c2w"], 20, 28, 0.0, 3.14, samples_per_ray=48,
+                                                 importance_samples_per_ray=40))
+    e_dep = np.abs(dep - f["van_depth"]).max()
+    assert np.abs(rgb - f["van_rgb"]).max() < TOL and e_dep <= util.gate(e_dep, fl[1]), (e_dep, fl)
     cap = cap_of(ref, f["cfg1_K"], f["cfg1_c2w"], 64, 64)
     rgb, dep = quiet(ref.render_utils.render_vanilla, coarse, cap, fine_net=None, rays_per_batch=2048, samples_per_ray=64,
                      return_depth=True)
     assert np.abs(rgb - f["cfg1_rgb"]).max() < TOL and np.abs(dep - f["cfg1_depth"]).max() < TOL
-    # a CPU model keeps the reference's own implementation (bit-identical to the golden it produced)
+    # a CPU model keeps the reference's own implementation (the golden it produced, up to the host's BLAS rounding)
     c_cpu, f_cpu = scenes.seed_nets(ref.vanilla.build_nerf, ref_opts.default_opt(use_cuda=False), 1)
     l0 = launches()
     cap = cap_of(ref, f["van_K"], f["van_c2w"], 20, 28)
     rgb = quiet(ref.render_utils.render_vanilla, c_cpu, cap, fine_net=f_cpu, rays_per_batch=100, samples_per_ray=48,
                 importance_samples_per_ray=40)
-    assert launches() == l0 and np.array_equal(rgb, f["van_rgb"])
+    assert launches() == l0 and np.abs(rgb - f["van_rgb"]).max() < 2e-6
 
 
 def test_reference_human_renderers_run_on_the_cuda_path(ref):
@@ -98,13 +103,21 @@ def test_reference_human_renderers_run_on_the_cuda_path(ref):
         close(a, f[f"smpl{can}_acc"], TOL, f"smpl{can} acc")
     r, d = quiet(ru.render_hybrid_nerf, net, cap, b1["verts"], b1["faces"], b1["Ts"], rays_per_batch=64, samples_per_ray=24,
                  importance_samples_per_ray=16, geo_threshold=geo, return_depth=True)
-    close(r, f["hyb_rgb"], TOL, "hybrid rgb")
-    close(d, f["hyb_depth"], 3 * TOL, "hybrid depth")
+    cb, fb, hp = (no.net_params_from_joiner(m) for m in (net.coarse_bkg_net, net.fine_bkg_net, net.coarse_human_net))
+    fl_h = util.floors16(lambda: no.render_hybrid_nerf(cb, fb, hp, f["h_K"], f["h_c2w"], H, W, 0.0, 3.14, b1["verts"], b1["faces"],
+                                                       b1["Ts"], samples_per_ray=24, importance_samples_per_ray=16,
+                                                       geo_threshold=geo)[:2])
+    close(r, f["hyb_rgb"], util.gate(0, fl_h[0]), "hybrid rgb")
+    close(d, f["hyb_depth"], util.gate(0, fl_h[1]), "hybrid depth")
     r, d = quiet(ru.render_hybrid_nerf_multi_persons, net, cap, [net, net], [b1["verts"], b2["verts"]], [b1["faces"]] * 2,
                  [b1["Ts"], b2["Ts"]], rays_per_batch=64, samples_per_ray=24, importance_samples_per_ray=16, geo_threshold=geo,
                  return_depth=True)
-    close(r, f["multi_rgb"], TOL, "multi rgb")
-    close(d, f["multi_depth"], 3 * TOL, "multi depth")
+    fl_m = util.floors16(lambda: no.render_hybrid_nerf_multi_persons(cb, fb, [hp, hp], f["h_K"], f["h_c2w"], H, W, 0.0, 3.14,
+                                                                     [b1["verts"], b2["verts"]], [b1["faces"]] * 2,
+                                                                     [b1["Ts"], b2["Ts"]], samples_per_ray=24,
+                                                                     importance_samples_per_ray=16, geo_threshold=geo))
+    close(r, f["multi_rgb"], util.gate(0, fl_m[0]), "multi rgb")
+    close(d, f["multi_depth"], util.gate(0, fl_m[1]), "multi depth")
     assert launches() > l0
 
 

