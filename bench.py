@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -310,6 +310,7 @@ def main():
     side = {}
     if not args.no_configs:
         side = side_configs(nb, render, sharding, scenes, ctx, dev, rank, world, dist, pk)
+    train = train_step_ms(nb, dev) if (world == 1 and not args.no_configs) else None
 
     if rank == 0:
         mlp_ms_per_launch = prof["mlp_ms"] / max(prof["mlp_launches"], 1)
@@ -336,7 +337,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": 208, "d2h_bytes_per_step": n_pix * 4 * 4,
                     "api": "neuman_b200.render_vanilla(coarse, cap, fine_net=fine, ...) -> numpy rgb [720,1280,3] + depth (reference signature); "
                            "inputs = the capture's K / camera_to_world (208 B host struct), rays are generated on the device"},
-            "gpu_launches": int(launches), "clocks": clocks, "configs": side,
+            "gpu_launches": int(launches), "clocks": clocks, "configs": side, "train_step": train,
         }
         if not args.no_cpu_baseline and world == 1:
             arm = CpuArm()
@@ -350,6 +351,34 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_step_ms(nb, dev, R=2048, steps=20):
+    """one optimiser step of the background-NeRF trainer (trainers/vanilla_nerf_trainer.py:206-223: loss_func
+    + backward + Adam) on the CUDA path at the reference's defaults (2048 rays, 128 + 128 samples, perturb 1, raw_noise_std 1)."""
+    import torch.nn.functional as F
+    from neuman_b200 import synthetic, train as nt
+    opt = nb.default_opt(perturb=1.0, raw_noise_std=1.0)
+    coarse, fine = synthetic.seed_nets(nb.build_nerf, nb.default_opt(use_cuda=False), 3)
+    coarse, fine = coarse.to(dev), fine.to(dev)
+    optim = torch.optim.Adam(list(coarse.parameters()) + list(fine.parameters()), lr=5e-4)
+    g = torch.Generator(device=dev).manual_seed(0)
+    batch = dict(origin=torch.randn(R, 3, device=dev, generator=g) * 0.1,
+                 direction=F.normalize(torch.randn(R, 3, device=dev, generator=g), dim=-1),
+                 near=torch.full((R,), 0.5, device=dev), far=torch.full((R,), 4.0, device=dev),
+                 color=torch.rand(R, 3, device=dev, generator=g))
+    for _ in range(5):
+        nt.train_batch(coarse, fine, optim, batch, opt, check_bad_weights=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = nt.train_batch(coarse, fine, optim, batch, opt, check_bad_weights=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "rays_per_s": R / ms * 1e3, "rays_per_batch": R, "samples": "128+128", "mlp_evals_per_step": R * 384,
+            "loss_finite": bool(torch.isfinite(loss)), "what": "neuman_b200.train.train_batch: CUDA forward/backward kernels + torch.optim.Adam"}
 
 
 def side_configs(nb, render, sharding, scenes, ctx, dev, rank, world, dist, pk):
@@ -385,29 +414,37 @@ def side_configs(nb, render, sharding, scenes, ctx, dev, rank, world, dist, pk):
         if name == "cfg2":
             cn, fn_ = model.coarse_bkg_net, model.fine_bkg_net
 
-            def fn():
+            def fn(ev=None):
                 rgb, depth, _ = part.buffers(with_acc=False)
                 render.render_vanilla_range(cn, cap, fn_, Sc, Nc, pixels=part.pixels, host_out=False, out=(rgb, depth))
+                if ev is not None:
+                    ev.record()
                 return part.gather()
         elif name.startswith("cfg3"):
             can = name.endswith("_can")
 
-            def fn():
+            def fn(ev=None):
                 bufs = part.buffers()
                 render.render_smpl_nerf_range(model, cap, bs[0]["verts"], faces, bs[0]["T"], Sc, True, can, geo, 1.0,
                                               pixels=part.pixels, host_out=False, out=bufs)
+                if ev is not None:
+                    ev.record()
                 return part.gather()
         elif name == "cfg4":
-            def fn():
+            def fn(ev=None):
                 bufs = part.buffers()
                 render.render_hybrid_nerf_range(model, cap, bs[0]["verts"], faces, bs[0]["T"], Sc, Nc, True, geo,
                                                 pixels=part.pixels, host_out=False, out=bufs)
+                if ev is not None:
+                    ev.record()
                 return part.gather()
         else:
-            def fn():
+            def fn(ev=None):
                 bufs = part.buffers()
                 render._hybrid(model, [model] * len(bs), cap, [b["verts"] for b in bs], [faces] * len(bs), [b["T"] for b in bs],
                                Sc, Nc, True, geo, True, 0, None, False, render.CHUNK, pixels=part.pixels, out=bufs)
+                if ev is not None:
+                    ev.record()
                 return part.gather()
         fn()
         torch.cuda.synchronize()
@@ -417,32 +454,35 @@ def side_configs(nb, render, sharding, scenes, ctx, dev, rank, world, dist, pk):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         reps = 2
-        for _ in range(reps):
-            fn()
+        fn()
+        eb, em = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eb.record()
+        fn(em)                                      # second frame: also stamp the end of this rank's own rendering
         e1.record()
         torch.cuda.synchronize()
+        busy_ms = eb.elapsed_time(em)
         prof = ctx.profile_read()
         ctx.profile(False)
         st = ctx.render_stats()
-        t = torch.tensor([e0.elapsed_time(e1) / reps, prof["mlp_ms"] / reps, float(st["mlp_evals"]), float(st["hit_rays"])],
+        t = torch.tensor([e0.elapsed_time(e1) / reps, prof["mlp_ms"] / reps, float(st["mlp_evals"]), float(st["hit_rays"]), busy_ms],
                          device=dev, dtype=torch.float64)
         if world > 1:
             tmax, tsum = t.clone(), t.clone()
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
             ms, mlp_ms, evals, hits = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tsum[3])
-            busy = [float(x) for x in _gather_scalars(dist, t[0], world, dev)]
+            busy = [float(x) for x in _gather_scalars(dist, t[4], world, dev)]
             hit_per_rank = [int(x) for x in _gather_scalars(dist, t[3], world, dev)]
         else:
-            ms, mlp_ms, evals, hits = (float(x) for x in t)
-            busy, hit_per_rank = [ms], [int(hits)]
+            ms, mlp_ms, evals, hits = (float(x) for x in t[:4])
+            busy, hit_per_rank = [busy_ms], [int(hits)]
         tf = evals / world * FLOP_PER_EVAL / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else None
         out[name] = {"driver": cfg["driver"] + (" render_can=True" if name.endswith("_can") else ""), "frame": f"{Wc}x{Hc}",
                      "samples": f"{Sc}+{Nc}", "ms_per_frame": ms, "Mrays_s": Hc * Wc / ms / 1e3, "mlp_evals": int(evals),
                      "hit_rays": int(hits), "mlp_ms": mlp_ms, "mlp_tflops_per_gpu": tf,
                      "mlp_frac_of_peak": tf / pk["tflops_sustained"] if tf else None,
                      "non_mlp_share": 1.0 - mlp_ms / ms if ms > 0 else None,
-                     "per_rank_ms": busy, "per_rank_hit_rays": hit_per_rank}
+                     "per_rank_render_ms": busy, "per_rank_hit_rays": hit_per_rank}
     return out
 
 

@@ -129,3 +129,69 @@ def test_large_weights_stay_finite(nets):
     assert torch.isfinite(y).all()
     rel = (y - ref).abs().max() / ref.abs().max()
     assert rel < 2e-3, rel
+
+
+def _emul_floor(net_cpu, pts, views):
+    """|fp32 oracle - oracle with 11-bit matmul operands| on these inputs: what the operand precision alone does."""
+    p = util.oracle_params(net_cpu)
+    with torch.no_grad():
+        ref = no.net_forward(p, pts, views)
+        with no.precision(operands="f16"):
+            emu = no.net_forward(p, pts, views)
+    return ref, float((emu - ref).abs().max())
+
+
+@pytest.mark.parametrize("kind", ["posenc", "rotate"])
+@pytest.mark.parametrize("xmax", [4.0, 30.0, 100.0])
+def test_large_coordinates(kind, xmax):
+    """|x| up to 100 for both encodings: the tensor-core path stays finite, its error stays within 3x what 11-bit operands do
+    to the oracle on the same inputs (the raw coordinates are input channels: their fp16 rounding grows with |x|), the fp32
+    mode within 2e-5 relative, and no range flag is raised (100 << 65504)."""
+    import copy
+    torch.manual_seed(int(xmax))
+    net, _ = util.scenes.seed_nets(nb.build_nerf, nb.default_opt(use_cuda=False, posenc=kind), 7)
+    n = 2048
+    pts = (torch.rand(n, 3) * 2 - 1) * xmax
+    views = torch.nn.functional.normalize(torch.randn(n, 3), dim=-1)
+    ref, floor = _emul_floor(copy.deepcopy(net), pts, views)
+    net = net.to(DEV)
+    ctx = _lib.Context.get(0)
+    ctx.range_check()                                            # clear
+    y = ops.joiner_forward(net, pts.to(DEV), views.to(DEV), mode=MODES["tc"]).cpu()
+    assert torch.isfinite(y).all()
+    assert (y - ref).abs().max() <= 3 * floor + 1e-4, (float((y - ref).abs().max()), floor)
+    ctx.range_check()                                            # raises if the flag were set
+    y32 = ops.joiner_forward(net, pts.to(DEV), views.to(DEV), mode=MODES["simt"]).cpu()
+    assert (y32 - ref).abs().max() <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("scale", [3.0, 10.0])
+def test_scaled_weights_and_the_range_flag(scale):
+    """Weights x3 (hidden activations grow to ~1e3: still in range) and x10 (1e8: beyond fp16).  In range, the error is that
+    of the operand precision (relative to the output scale); out of range the packs saturate -- finite outputs -- and
+    nm_range_status reports NM_ERR_RANGE, once (the flag is cleared by the call), while the fp32 mode is unaffected."""
+    import copy
+    torch.manual_seed(3)
+    net, _ = util.scenes.seed_nets(nb.build_nerf, nb.default_opt(use_cuda=False), 11)
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if name.endswith("weight"):
+                p.mul_(scale)
+    n = 3000
+    pts, views = torch.randn(n, 3), torch.nn.functional.normalize(torch.randn(n, 3), dim=-1)
+    ref, floor = _emul_floor(copy.deepcopy(net), pts, views)
+    net = net.to(DEV)
+    ctx = _lib.Context.get(0)
+    ctx.range_check()
+    y = ops.joiner_forward(net, pts.to(DEV), views.to(DEV), mode=MODES["tc"]).cpu()
+    assert torch.isfinite(y).all()
+    hidden_max = float(ref.abs().max())
+    if scale <= 3.0:
+        assert (y - ref).abs().max() <= 3 * floor + 1e-4 * max(1.0, hidden_max), (float((y - ref).abs().max()), floor)
+        ctx.range_check()
+    else:
+        with pytest.raises(_lib.NmError, match="range"):
+            ctx.range_check()
+        ctx.range_check()                                        # cleared by the failing call
+        y32 = ops.joiner_forward(net, pts.to(DEV), views.to(DEV), mode=MODES["simt"]).cpu()
+        assert torch.isfinite(y32).all() and (y32 - ref).abs().max() <= 1e-4 * max(1.0, hidden_max)
