@@ -61,6 +61,7 @@ extern "C" int nm_ctx_destroy(nm_ctx* ctx) {
   if (ctx->can64) cudaFree(ctx->can64);
   if (ctx->face_tmp) cudaFree(ctx->face_tmp);
   for (auto e : ctx->prof_events) cudaEventDestroy(e);
+  if (ctx->ev_counts) cudaEventDestroy(ctx->ev_counts);
   if (ctx->d_counter) cudaFree(ctx->d_counter);
   if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
   delete ctx;

@@ -85,6 +85,7 @@ struct nm_ctx {
   uint32_t range_seq = 0;         // launch counter of the tensor-core MLP (rotates the phase of its sampled range check)
   int32_t* d_counter = nullptr;   // small device scratch (compaction counters)
   int32_t* h_counter = nullptr;   // pinned host mirror
+  cudaEvent_t ev_counts = nullptr;   // marks the hit counts' arrival on the host (render.cu)
   double* can64 = nullptr;        // float64 canonical points scratch (warp.cu)
   // optional per-launch timing of the MLP kernel (bench.py roofline): event pairs on the launch stream
   bool profile = false;

@@ -83,6 +83,13 @@ __global__ void k_mark_rows(const int32_t* __restrict__ idx, long long n, float*
   if (t < n) flag[idx[t]] = 1.f;
 }
 
+// flag[r] = 1 for the rays of a near/far pair that hit (near < far)
+__global__ void k_mark_hits(const float* __restrict__ near_v, const float* __restrict__ far_v, long long R,
+                            float* __restrict__ flag) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < R && near_v[r] < far_v[r]) flag[r] = 1.f;
+}
+
 __global__ void k_fill(float* __restrict__ p, long long n, float v) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) p[t] = v;
@@ -294,14 +301,15 @@ extern "C" int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int
   const int Sm = Sb + n_actors * S;
   const int64_t C = std::min<int64_t>(chunk_of(opt), n > 0 ? n : 1);
   ctx->last_mlp_evals = 0; ctx->last_hit_rays = 0;
-  size_t per_ray = 6 + 2 + 1 + 8 + 9 * S + (size_t)5 * S + 6 * S + 5 * Sb + 5 * Sb + 5 * Sm + 8 + 5 +
+  size_t per_ray = 6 + 2 + 1 + 8 + 9 * S + (size_t)5 * S + 6 * S + 5 * Sb + 5 * Sb + 5 * Sm + 8 + 5 + 3 * (size_t)n_actors +
                    (multi_person ? (size_t)10 * S * n_actors + 2 : 0);
-  size_t bytes = (size_t)C * per_ray * sizeof(float) + 64 * 256;
+  size_t bytes = (size_t)C * per_ray * sizeof(float) + 96 * 256;
   Arena A;
   TRY(nm_impl_workspace(ctx, bytes, &A.base));
   float* o = A.take<float>(3 * C); float* d = A.take<float>(3 * C);
-  float* nr = A.take<float>(C); float* fr = A.take<float>(C);
-  int32_t* hit = A.take<int32_t>(C);
+  float* nr_a[NM_MAX_ACTORS]; float* fr_a[NM_MAX_ACTORS]; int32_t* hit_a[NM_MAX_ACTORS];
+  for (int a = 0; a < n_actors; ++a) { nr_a[a] = A.take<float>(C); fr_a[a] = A.take<float>(C); hit_a[a] = A.take<int32_t>(C); }
+  int32_t* hit = A.take<int32_t>(C);                                                // rays any actor hits (multi-person)
   float* oh = A.take<float>(3 * C); float* dh = A.take<float>(3 * C); float* nh = A.take<float>(C); float* fh = A.take<float>(C);
   float* pts = A.take<float>(3 * C * S); float* cpts = A.take<float>(3 * C * S); float* cdirs = A.take<float>(3 * C * S);
   float* z_h = A.take<float>(C * S); float* raw_h = A.take<float>(4 * C * S);
@@ -323,23 +331,38 @@ extern "C" int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int
   }
 
   if (A.off > ctx->ws_bytes) NM_FAIL(ctx, NM_ERR_STATE, "render: workspace arena overflow (internal sizing bug)");
+  if (!ctx->ev_counts) NM_CHECK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_counts, cudaEventDisableTiming));
   for (int64_t i = 0; i < n; i += C) {
     int64_t c = std::min<int64_t>(C, n - i);
     TRY(nm_impl_raygen(ctx, cam, 0, pix0 + i, c, nullptr, pixels ? pixels + i : nullptr, o, d, st));                        // shot_rays (:271 / :386)
+    // Hit lists of every actor (:299 / :415) and, for several actors, of their union FIRST: the counts travel to the host
+    // while the background networks run, so the host never waits for them with the GPU idle.
+    int64_t Rh_a[NM_MAX_ACTORS]; int64_t Ru = 0;
+    NM_CHECK_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int32_t) * (n_actors + 1), st));
+    if (multi_person) { LAUNCH1D(k_fill, c, st, flag, c, 0.f); LAUNCH1D(k_fill, c, st, zeros, c, 0.f); }
+    for (int a = 0; a < n_actors; ++a) {
+      TRY(nm_impl_near_far_mesh(ctx, ctx->meshes[actors[a]], o, d, c, opt->geo_threshold, nr_a[a], fr_a[a], st));
+      LAUNCH1D(k_compact_hits, c, st, nr_a[a], fr_a[a], c, hit_a[a], ctx->d_counter + a);
+      if (multi_person) LAUNCH1D(k_mark_hits, c, st, nr_a[a], fr_a[a], c, flag);
+    }
+    if (multi_person) LAUNCH1D(k_compact_hits, c, st, zeros, flag, c, hit, ctx->d_counter + n_actors);
+    NM_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->h_counter, ctx->d_counter, sizeof(int32_t) * (n_actors + 1), cudaMemcpyDeviceToHost, st));
+    NM_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_counts, st));
     float *raw_b, *z_b; int St;
     TRY(bkg_pass(ctx, coarse_slot, fine_slot, opt, o, d, c, z_c, raw_c, w_c, z_f, raw_f, &raw_b, &z_b, &St, st));
+    NM_CHECK_CUDA(ctx, cudaEventSynchronize(ctx->ev_counts));
+    for (int a = 0; a < n_actors; ++a) { Rh_a[a] = ctx->h_counter[a]; ctx->last_hit_rays += Rh_a[a]; }
+    Ru = ctx->h_counter[n_actors];
     float* rgb_dst = host_out ? rgb_s : rgb + 3 * i;
     float* dep_dst = host_out ? dep_s : (depth ? depth + i : dep_s);
     float* acc_dst = host_out ? acc_s : (acc ? acc + i : acc_s);
     if (!multi_person) {
-      const NmMesh& mesh = ctx->meshes[actors[0]];
       // all rays first get the background-only composite (miss rays keep it, :301-311)
       TRY(nm_raw2outputs(ctx, raw_b, z_b, d, c, St, nullptr, 1.f, opt->white_bkg, rgb_dst, nullptr, nullptr, nullptr, dep_dst, st));
       LAUNCH1D(k_fill, c, st, acc_dst, c, 0.f);
-      TRY(nm_impl_near_far_mesh(ctx, mesh, o, d, c, opt->geo_threshold, nr, fr, st));   // (:299)
-      int64_t Rh = 0;
-      TRY(compact(ctx, nr, fr, c, hit, &Rh, st));
-      ctx->last_hit_rays += Rh;
+      const int64_t Rh = Rh_a[0];
+      const int32_t* hit = hit_a[0];
+      const float *nr = nr_a[0], *fr = fr_a[0];
       if (Rh > 0) {
         LAUNCH1D(k_gather_rays, Rh, st, hit, (int)Rh, o, d, nr, fr, oh, dh, nh, fh);
         TRY(human_branch(ctx, human_slots[0], actors[0], opt, oh, dh, nh, fh, Rh, pts, cpts, cdirs, z_h, raw_h, false, st));
@@ -362,25 +385,16 @@ extern "C" int nm_render_hybrid(nm_ctx* ctx, int coarse_slot, int fine_slot, int
       // composite is the background composite whose last interval ends at the first placeholder (z = 2 far), no
       // sort needed.  Rays at least one actor hits go through the full z-sorted merge (:441-448), compacted.
       TRY(nm_impl_raw2outputs_zend(ctx, raw_b, z_b, d, c, St, opt->white_bkg, opt->far_bkg * 2.f, rgb_dst, dep_dst, st));
-      LAUNCH1D(k_fill, c, st, flag, c, 0.f);
-      LAUNCH1D(k_fill, c, st, zeros, c, 0.f);
       for (int a = 0; a < n_actors; ++a) {
-        const NmMesh& mesh = ctx->meshes[actors[a]];
         LAUNCH1D(k_fill_placeholder, c * S, st, z_a[a], (float4*)raw_a[a], c, S, opt->far_bkg * 2.f, opt->far_bkg * 3.f);
-        TRY(nm_impl_near_far_mesh(ctx, mesh, o, d, c, opt->geo_threshold, nr, fr, st));   // (:415)
-        int64_t Rh = 0;
-        TRY(compact(ctx, nr, fr, c, hit, &Rh, st));
-        ctx->last_hit_rays += Rh;
+        const int64_t Rh = Rh_a[a];
         if (Rh > 0) {
-          LAUNCH1D(k_gather_rays, Rh, st, hit, (int)Rh, o, d, nr, fr, oh, dh, nh, fh);
+          LAUNCH1D(k_gather_rays, Rh, st, hit_a[a], (int)Rh, o, d, nr_a[a], fr_a[a], oh, dh, nh, fh);
           TRY(human_branch(ctx, human_slots[a], actors[a], opt, oh, dh, nh, fh, Rh, pts, cpts, cdirs, z_h, raw_h, false, st));
-          LAUNCH1D(k_move_rows, Rh * S, st, hit, Rh, S, z_h, z_a[a], 1);                 // (:438-439)
-          LAUNCH1D(k_move_rows, Rh * S * 4, st, hit, Rh, S * 4, raw_h, raw_a[a], 1);
-          LAUNCH1D(k_mark_rows, Rh, st, hit, Rh, flag);
+          LAUNCH1D(k_move_rows, Rh * S, st, hit_a[a], Rh, S, z_h, z_a[a], 1);              // (:438-439)
+          LAUNCH1D(k_move_rows, Rh * S * 4, st, hit_a[a], Rh, S * 4, raw_h, raw_a[a], 1);
         }
       }
-      int64_t Ru = 0;
-      TRY(compact(ctx, zeros, flag, c, hit, &Ru, st));                                   // rays with flag > 0
       if (Ru > 0) {
         const float* zl[1 + NM_MAX_ACTORS]; const float* rl[1 + NM_MAX_ACTORS]; int32_t Sl[1 + NM_MAX_ACTORS];
         LAUNCH1D(k_gather_rays, Ru, st, hit, (int)Ru, o, d, zeros, flag, oh, dh, nh, fh);

@@ -240,12 +240,31 @@ __device__ __forceinline__ int bvh_nearest_face(const BvhView& B, V3<float> p, i
 
 // The search and the float64 evaluation are two kernels: the traversal is a latency-bound pointer chase that wants many
 // resident warps (fp32, ~40 registers), the evaluation needs ~80 registers of float64 state.
-__global__ void __launch_bounds__(128) k_warp_nearest(BvhView B, const float* __restrict__ pts, long long n,
+// Packet shape: the 32 lanes of a warp take (1 << lg_rays) neighbouring rays x (32 >> lg_rays) consecutive samples, so the
+// packet is a compact bundle instead of a long stretch of one ray and the union of the nodes its lanes need is small.
+// The result per point does not depend on the packet it travels in (every node a lane needs is visited, ties go to the
+// lowest face index).  lg_rays = 0 is the plain linear order (any S).
+__global__ void __launch_bounds__(128) k_warp_nearest(BvhView B, const float* __restrict__ pts, long long R, int S, int lg_rays,
                                                        int32_t* __restrict__ face_out) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < n;
-  const long long ii = live ? i : n - 1;
-  V3<float> p{pts[3 * ii], pts[3 * ii + 1], pts[3 * ii + 2]};
+  const long long w = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  long long i;
+  bool live;
+  if (lg_rays == 0) {
+    i = w * 32 + lane;
+    live = i < R * S;
+    if (!live) i = R * S - 1;
+  } else {
+    const int per = 32 >> lg_rays;                       // samples of one ray in the packet
+    const int groups = S / per;                          // packets along a ray (S % per == 0, checked by the host)
+    const long long rg = w / groups;
+    const int sg = (int)(w - rg * groups);
+    long long ray = (rg << lg_rays) + (lane / per);
+    live = ray < R;
+    if (!live) ray = R - 1;
+    i = ray * S + sg * per + (lane % per);
+  }
+  V3<float> p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
   __shared__ int s_stack[4][64];
   const int best_f = bvh_nearest_face(B, p, s_stack[threadIdx.x >> 5]);
   if (live) face_out[i] = best_f;
@@ -444,8 +463,14 @@ extern "C" int nm_warp_to_canonical(nm_ctx* ctx, int actor, const float* pts, in
     }
     fid = ctx->face_tmp;
   }
-  k_warp_nearest<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, pts, n, fid);
-  NM_CHECK_LAUNCH(ctx);
+  {
+    static const int lg_env = [] { const char* e = getenv("NEUMAN_WARP_PACKET"); return e ? atoi(e) : -1; }();
+    int lg = (lg_env >= 0 && lg_env <= 3) ? lg_env : 1;   // default: 2 rays x 16 samples (profiles/r02_configs.md)
+    while (lg > 0 && (S % (32 >> lg) != 0 || R < (1 << lg))) --lg;
+    long long warps = lg == 0 ? (n + 31) / 32 : ((R + (1 << lg) - 1) >> lg) * (long long)(S / (32 >> lg));
+    k_warp_nearest<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(B, pts, (long long)R, (int)S, lg, fid);
+    NM_CHECK_LAUNCH(ctx);
+  }
   k_warp_points<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(m.verts, m.faces, m.T, pts, n, fid, can64, closest);
   NM_CHECK_LAUNCH(ctx);
   k_warp_dirs<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(can64, R, S, can_pts, can_dirs);
