@@ -96,18 +96,36 @@ def near_far_cache_device(cap, verts, geo_threshold=ops.DEFAULT_GEO_THRESH, devi
     return torch.stack([near.reshape(H, W), far.reshape(H, W)], -1)
 
 
+PATCH_SIZE = 32                      # utils/constant.py:8
+PATCH_SIZE_SQUARED = PATCH_SIZE ** 2
+
+
+def get_left_upper_corner(h, w, pos, size=PATCH_SIZE):
+    """datasets/human_rays.py:18-34: left upper corner (x, y) of a size x size patch centred (as centred as the image
+    allows) at pos = (x, y)."""
+    lu_x = min(max(int(pos[0]) - size // 2, 0), w - size)
+    lu_y = min(max(int(pos[1]) - size // 2, 0), h - size)
+    return lu_x, lu_y
+
+
 class HumanRayBatcher:
-    """`HumanRayDataset.__getitem__` (datasets/human_rays.py:100-247) on the device, without the LPIPS patch branch
-    (opt.penalize_lpips must be 0: the LPIPS network is not part of this repo).  caps: captures with .image, .mask,
-    .binary_mask, .border_mask (when opt.dilation > 0), .near/.far {'bkg','human'}, .frame_id and the camera;
-    near_far: one [H,W,>=2] array/tensor per capture (near_far_cache_device, or the reference's .npy cache)."""
+    """`HumanRayDataset.__getitem__` (datasets/human_rays.py:100-247) on the device, including the 32x32 patch branch
+    that the LPIPS term of the human trainer needs (opt.penalize_lpips > 0, :114-126, :163-183; the LPIPS network itself is
+    the caller's).  caps: captures with .image, .mask, .binary_mask, .border_mask (when opt.dilation > 0), .near/.far
+    {'bkg','human'}, .frame_id and the camera; near_far: one [H,W,>=2] array/tensor per capture (near_far_cache_device, or
+    the reference's .npy cache).
+
+    A batch is a list of segments (ray_key, pixels) in the reference's order: with a patch, the first PATCH_SIZE_SQUARED
+    rays are the patch in row-major order (or, when the coin of :122 falls the other way, a body/border/background split of
+    the same size), followed by the split of the remaining rays."""
 
     KEYS = ('num_body_rays', 'num_border_rays', 'num_bkg_rays')
 
     def __init__(self, opt, caps, near_far, device="cuda"):
-        if getattr(opt, 'penalize_lpips', 0) > 0:
-            raise NotImplementedError("patch sampling for the LPIPS loss is not on the built path")
         self.opt, self.batch_size, self.device = opt, int(opt.rays_per_batch), torch.device(device)
+        self.num_patch = 1 if getattr(opt, 'penalize_lpips', 0) > 0 else 0          # (:72)
+        if self.num_patch:
+            assert self.batch_size > PATCH_SIZE_SQUARED                               # (:117)
         self.caps = list(caps)
         self.lut = torch.from_numpy((np.arange(256) / 255).astype(np.float32)).to(self.device)
         self.images, self.binary, self.cache, self.sets = [], [], [], []
@@ -135,23 +153,54 @@ class HumanRayBatcher:
         assert arr.min() >= 0 and arr.sum() == num
         return dict(zip(self.KEYS, (int(a) for a in arr)))
 
-    def sample_coords(self, cap_index, generator=None):
-        out = {}
-        for key, num in self.get_num_rays_dict(self.batch_size).items():
+    def plan(self, need_patch):
+        """The (ray_key, count) segments of one batch (:112-126, :145-152)."""
+        bins = [self.batch_size] if self.num_patch == 0 else [PATCH_SIZE_SQUARED, self.batch_size - PATCH_SIZE_SQUARED]
+        segs = []
+        for i, num in enumerate(bins):
             if num == 0:
                 continue
-            pool = self.sets[cap_index][key]
-            out[key] = pool[torch.randint(0, pool.shape[0], (num,), device=self.device, generator=generator)]
+            if self.num_patch == 1 and need_patch and i == 0:
+                segs.append(('num_patch_rays', num))
+            else:
+                segs += [(k, n) for k, n in self.get_num_rays_dict(num).items() if n > 0]
+        return segs
+
+    def patch_coords(self, cap_index, seed_xy):
+        """The PATCH_SIZE x PATCH_SIZE pixels around seed_xy = (x, y) in row-major order as [n,2] (x, y) (:163-183)."""
+        h, w = self.images[cap_index].shape[:2]
+        lu_x, lu_y = get_left_upper_corner(h, w, seed_xy)
+        ys = torch.arange(lu_y, lu_y + PATCH_SIZE, device=self.device, dtype=torch.int32)
+        xs = torch.arange(lu_x, lu_x + PATCH_SIZE, device=self.device, dtype=torch.int32)
+        return torch.stack([xs[None, :].expand(PATCH_SIZE, -1), ys[:, None].expand(-1, PATCH_SIZE)], -1).reshape(-1, 2).contiguous()
+
+    def sample_coords(self, cap_index, generator=None, need_patch=None):
+        """The random part: returns [(ray_key, [num,2] (x, y) int32), ...]."""
+        if need_patch is None:
+            need_patch = bool(np.random.random() < self.opt.body_rays_ratio)        # random.random() < body_rays_ratio (:122)
+        out = []
+        for key, num in self.plan(need_patch):
+            if key == 'num_patch_rays':
+                pool = self.sets[cap_index]['num_body_rays']                        # random.choice(argwhere(mask != 0)) (:163)
+                seed = pool[torch.randint(0, pool.shape[0], (1,), device=self.device, generator=generator)][0].tolist()
+                out.append((key, self.patch_coords(cap_index, seed)))
+            else:
+                pool = self.sets[cap_index][key]
+                out.append((key, pool[torch.randint(0, pool.shape[0], (num,), device=self.device, generator=generator)]))
         return out
 
     def batch_from_coords(self, cap_index, coords):
-        """The deterministic part (:176-247) for given pixels {ray_key: [num,2] (x, y)}."""
+        """The deterministic part (:176-247) for given pixels: [(ray_key, [num,2] (x, y)), ...] in batch order (or a
+        {ray_key: pixels} dict, taken in KEYS order)."""
+        if isinstance(coords, dict):
+            coords = [(k, coords[k]) for k in self.KEYS if coords.get(k) is not None]
         cap, img, cache = self.caps[cap_index], self.images[cap_index], self.cache[cap_index]
         cols, origs, dirs, hn, hf, bn, bf, isb, hit = [], [], [], [], [], [], [], [], []
-        for key in self.KEYS:
-            xy = coords.get(key)
+        patch_counter = 0
+        for key, xy in coords:
             if xy is None or xy.shape[0] == 0:
                 continue
+            patch_counter += int(key == 'num_patch_rays')
             x, y = xy[:, 0].long(), xy[:, 1].long()
             num = xy.shape[0]
             cols.append(self.lut[img[y, x].long()])
@@ -171,9 +220,9 @@ class HumanRayBatcher:
                 'human_near': torch.cat(hn), 'human_far': torch.cat(hf), 'bkg_near': torch.cat(bn), 'bkg_far': torch.cat(bf),
                 'is_bkg': torch.cat(isb), 'is_hit': torch.cat(hit),
                 'cur_view_f': fid['frame_id'] / fid['total_frames'], 'cur_view': fid['frame_id'], 'cap_id': cap_index,
-                'patch_counter': torch.tensor(0)}
+                'patch_counter': torch.tensor(patch_counter)}
 
-    def __call__(self, cap_index=None, generator=None):
+    def __call__(self, cap_index=None, generator=None, need_patch=None):
         if cap_index is None:
             cap_index = int(np.random.randint(len(self.caps)))          # random.choice(self.inclusions) (:105)
-        return self.batch_from_coords(cap_index, self.sample_coords(cap_index, generator))
+        return self.batch_from_coords(cap_index, self.sample_coords(cap_index, generator, need_patch))

@@ -6,6 +6,7 @@ import torch
 
 from neuman_b200 import autograd as nag
 from oracle import neuman_oracle as no
+from tests import util
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -366,7 +367,7 @@ def test_human_ray_batcher():
                                 bkg_rays_ratio=0.3)
     b = nd.HumanRayBatcher(opt, [cap], [nf])
     assert b.get_num_rays_dict(300) == {'num_body_rays': 180, 'num_border_rays': 30, 'num_bkg_rays': 90}
-    coords = b.sample_coords(0)
+    coords = dict(b.sample_coords(0, need_patch=False))
     c = {k: v.cpu().numpy() for k, v in coords.items()}
     assert (cap.mask[c['num_body_rays'][:, 1], c['num_body_rays'][:, 0]] != 0).all()
     assert (cap.border_mask[c['num_border_rays'][:, 1], c['num_border_rays'][:, 0]] == 1).all()
@@ -395,6 +396,117 @@ def test_human_ray_batcher():
         assert np.array_equal(g, r.astype(g.dtype)), k
     assert out['is_bkg'].dtype == torch.long and out['is_hit'].dtype == torch.long and out['origin'].shape == (300, 3)
     assert out['cur_view'] == 3 and abs(out['cur_view_f'] - 3 / 11) < 1e-12 and out['cap_id'] == 0
+
+
+def _golden_caps(g, prefix, n):
+    """SimpleCaptures rebuilt from the arrays tools/make_golden_batches.py stored next to the reference's batches."""
+    from neuman_b200.render import SimpleCapture
+    caps = []
+    for i in range(n):
+        p = f"{prefix}{i}_"
+        H, W = g[p + "image"].shape[:2]
+        nf = g[p + "near_far"]
+        cap = SimpleCapture(g[p + "K"], g[p + "c2w"], H, W, near=float(nf[0]), far=float(nf[1]))
+        cap.near['human'], cap.far['human'] = float(nf[2]), float(nf[3])
+        cap.image, cap.mask, cap.binary_mask = g[p + "image"], g[p + "mask"], g[p + "binary_mask"]
+        cap.depth_map, cap.fused_depth_map = g[p + "depth_map"], g[p + "fused_depth_map"]
+        if p + "border_mask" in g:
+            cap.border_mask = g[p + "border_mask"]
+        cap.frame_id = {'frame_id': int(g[p + "frame"][0]), 'total_frames': int(g[p + "frame"][1])}
+        caps.append(cap)
+    return caps
+
+
+def _same_batch(out, g, tag, ray_tol=2e-6):
+    for key in [k[len(tag) + 5:] for k in g if k.startswith(tag + "_out_")]:
+        want, got = g[f"{tag}_out_{key}"], out[key]
+        got = got.cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+        assert got.shape == want.shape, (tag, key, got.shape, want.shape)
+        if key in ('origin', 'direction'):
+            assert np.abs(got - want).max() < ray_tol, (tag, key)
+        elif want.dtype.kind == 'f':
+            assert np.array_equal(got.astype(want.dtype), want), (tag, key)
+        else:
+            assert np.array_equal(got.astype(np.int64), want.astype(np.int64)), (tag, key)
+            if isinstance(out[key], torch.Tensor) and want.ndim:
+                assert out[key].dtype == torch.long, (tag, key)
+
+
+def test_background_batches_equal_the_reference_dataset():
+    """neuman_b200.data.BackgroundRayBatcher on the pixels the UNMODIFIED BackgroundRayDataset.__getitem__
+    (datasets/background_rays.py:41-139) drew, against the batch it returned (tests/golden/batches.npz,
+    tools/make_golden_batches.py): plain, fused depth, NeRF-T ablation sampling."""
+    import types
+    from neuman_b200 import data as nd
+    g = util.golden("batches.npz")
+    caps = _golden_caps(g, "bg_cap", 3)
+    for tag, fused, nerft in (("bg", False, False), ("bgf", True, False), ("bgt", False, True)):
+        opt = types.SimpleNamespace(rays_per_batch=500, use_fused_depth=fused, ablate_nerft=nerft)
+        b = nd.BackgroundRayBatcher(opt, caps)
+        bins, xy = g[tag + "_bins"], g[tag + "_coords"]
+        coords, at = [], 0
+        for n in bins:
+            coords.append(None if n == 0 else torch.from_numpy(np.ascontiguousarray(xy[at:at + n], dtype=np.int32)).cuda())
+            at += int(n)
+        _same_batch(b.batch_from_coords(coords), g, tag)
+        # the random part draws from the same admissible sets as the reference did
+        if not nerft:
+            for cap, c in zip(caps, b.sample_coords()):
+                if c is not None:
+                    c = c.cpu().numpy()
+                    bad = cap.mask[c[:, 1], c[:, 0]] != 0
+                    if hasattr(cap, 'border_mask'):
+                        bad |= cap.border_mask[c[:, 1], c[:, 0]] != 0
+                    assert not bad.any()
+
+
+def test_human_batches_equal_the_reference_dataset():
+    """neuman_b200.data.HumanRayBatcher against the UNMODIFIED HumanRayDataset.__getitem__ (datasets/human_rays.py:100-247)
+    on the same pixels and the same near/far cache: no patch (penalize_lpips = 0), patch taken, patch branch enabled but the
+    coin of :122 falling on a plain split.  Then the device near/far cache against the reference's
+    (data_io/cache_helper.py:16-36) and the shape of a freshly sampled patch."""
+    import types
+    from neuman_b200 import data as nd
+    g = util.golden("batches.npz")
+    caps = _golden_caps(g, "hu_cap", 2)
+    cache = [g["hu_cap0_cache"], g["hu_cap1_cache"]]
+    for tag, lp in (("hu", 0.0), ("hup", 0.1), ("hun", 0.1)):
+        opt = types.SimpleNamespace(rays_per_batch=1400, penalize_lpips=lp, dilation=5, body_rays_ratio=0.6,
+                                    border_rays_ratio=0.1, bkg_rays_ratio=0.3)
+        b = nd.HumanRayBatcher(opt, caps, cache)
+        segs = b.plan(need_patch=(tag == "hup"))
+        assert [n for _, n in segs] == [int(n) for n in g[tag + "_seg"]], (tag, segs)
+        xy, at, coords = g[tag + "_coords"], 0, []
+        for key, n in segs:
+            coords.append((key, torch.from_numpy(np.ascontiguousarray(xy[at:at + n], dtype=np.int32)).cuda()))
+            at += n
+        out = b.batch_from_coords(int(g[tag + "_cap"]), coords)
+        _same_batch(out, g, tag)
+        assert int(out['patch_counter']) == int(g[tag + "_out_patch_counter"])
+    # the reference's patch is what patch_coords builds around the same corner
+    b = nd.HumanRayBatcher(types.SimpleNamespace(rays_per_batch=1400, penalize_lpips=0.1, dilation=5, body_rays_ratio=0.6,
+                                                 border_rays_ratio=0.1, bkg_rays_ratio=0.3), caps, cache)
+    ref_patch = g["hup_coords"][:1024]
+    centre = (int(ref_patch[0, 0]) + 16, int(ref_patch[0, 1]) + 16)
+    assert np.array_equal(b.patch_coords(1, centre).cpu().numpy(), ref_patch)
+    for need in (True, False):
+        segs = b.sample_coords(1, need_patch=need)
+        assert sum(x.shape[0] for _, x in segs) == 1400 and (segs[0][0] == 'num_patch_rays') == need
+        if need:
+            p = segs[0][1].cpu().numpy().reshape(32, 32, 2)
+            H, W = caps[1].image.shape[:2]
+            assert (np.diff(p[..., 0], axis=1) == 1).all() and (np.diff(p[..., 1], axis=0) == 1).all()
+            assert p.min() >= 0 and p[..., 0].max() < W and p[..., 1].max() < H
+    assert nd.get_left_upper_corner(56, 64, (2, 55)) == (0, 24) and nd.get_left_upper_corner(56, 64, (63, 3)) == (32, 0)
+    # device near/far cache of the same captures against the reference's cache (float32 rays at distance ~1.5)
+    from oracle import synth_smpl
+    body = synth_smpl.random_body(seed=1, center=(0.1, -0.05, -0.2))
+    for cap, want in zip(caps, cache):
+        got = nd.near_far_cache_device(cap, body["verts"], body["geo_threshold"]).cpu().numpy()
+        solid = (want[..., 0] < want[..., 1]) & ((want[..., 1] - want[..., 0]) > 1e-3)
+        miss = np.isinf(want[..., 0])
+        assert solid.sum() > 100 and ((got[..., 0] < got[..., 1]) == (want[..., 0] < want[..., 1]))[solid | miss].all()
+        assert np.abs(got[solid] - want[solid]).max() < 1e-4
 
 
 def test_training_empty_and_scale_and_additivity():

@@ -203,3 +203,29 @@ def test_frame_metrics_match_the_oracle(tmp_path):
     assert np.array_equal(np.asarray(Image.open(tmp_path / "a.png")), u)
     r = metrics.eval_metrics([gt, gt], [pred, gt])
     assert set(r) == {"ssim", "psnr"} and np.isinf(r["psnr"])
+
+
+def test_batchers_host_logic_equals_the_reference_datasets(monkeypatch):
+    """The host logic of neuman_b200.data (segment plan, patch window, gathers, near/far cache lookup, dtypes) on CPU
+    tensors against the batches the UNMODIFIED reference datasets produced (tests/golden/batches.npz): the ray kernel
+    (ops.shot_rays -> nm_raygen) is substituted by the oracle here; tests/test_gpu_train.py runs the same comparison
+    through the CUDA library."""
+    import numpy as np
+    import torch
+    from neuman_b200 import data as nd, ops
+    from oracle import neuman_oracle as no
+    from tests import test_gpu_train as T, util
+
+    def oracle_shot_rays(cap, xy, device=None):
+        o, d = no.shot_rays(cap.intrinsic_matrix, cap.cam_pose.camera_to_world, xy.cpu().numpy())
+        return torch.from_numpy(np.asarray(o, dtype=np.float32)), torch.from_numpy(np.asarray(d, dtype=np.float32))
+    g = util.golden("batches.npz")
+    B, H = nd.BackgroundRayBatcher, nd.HumanRayBatcher
+    monkeypatch.setattr(ops, "shot_rays", oracle_shot_rays)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(nd, "BackgroundRayBatcher", lambda opt, caps: B(opt, caps, device="cpu"))
+    monkeypatch.setattr(nd, "HumanRayBatcher", lambda opt, caps, nf: H(opt, caps, nf, device="cpu"))
+    monkeypatch.setattr(nd, "near_far_cache_device",
+                        lambda cap, verts, thr: torch.from_numpy(g["hu_cap%d_cache" % (0 if cap.image.shape[0] == 48 else 1)]))
+    T.test_background_batches_equal_the_reference_dataset()
+    T.test_human_batches_equal_the_reference_dataset()
