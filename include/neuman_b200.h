@@ -240,6 +240,45 @@ int nm_smpl_scene_transforms(nm_ctx* ctx, const nm_smpl_model* model, const floa
                              const float* betas, const double* alignment, double scale, double* T_da2scene,
                              float* world_verts, void* stream);
 
+/* ---- human trainer: differentiable observation -> canonical map ------------------------------- */
+/* warp_samples_to_canonical_diff (utils/ray_utils.py:69-93) after its igl.signed_distance call (:70; here
+ * nm_signed_distance): f_id [n] closest face and closest [n,3] f64 closest point of every sample (constants of the step,
+ * as in the reference), verts [V,3] f32, faces [F,3] int32, T [V,4,4] f32 (HumanNeRF.vertex_forward's raw_Ts)
+ * -> Tinv [n,4,4] f32 = inverse of the barycentric blend of the three vertex transforms (:72-91). */
+int nm_warp_diff_forward(nm_ctx* ctx, const int32_t* f_id, const double* closest, const float* verts,
+                         const int32_t* faces, const float* T, int64_t n, float* Tinv, void* stream);
+/* What torch autograd computes for those lines in loss.backward() (trainers/human_nerf_trainer.py:205): g_Tinv [n,4,4]
+ * -> g_T [n_verts,4,4] (through blend and inverse) and g_verts [n_verts,3] (through the barycentric coordinates).
+ * Both outputs are overwritten (zeroed, then accumulated with atomics); either may be NULL. */
+int nm_warp_diff_backward(nm_ctx* ctx, const int32_t* f_id, const double* closest, const float* verts,
+                          const int32_t* faces, const float* T, int64_t n, const float* g_Tinv, int32_t n_verts,
+                          float* g_T, float* g_verts, void* stream);
+/* The same map fused with what the trainer does next (trainers/human_nerf_trainer.py:272-276): pts [R,S,3] ->
+ * can_pts = (Tinv @ [pts;1])[:3] + offset (offset [R,S,3] or NULL) and can_dirs = unit differences of consecutive
+ * canonical points along the ray, the last sample repeating the previous direction (may be NULL).  S >= 2. */
+int nm_human_canonicalize(nm_ctx* ctx, const int32_t* f_id, const double* closest, const float* verts,
+                          const int32_t* faces, const float* T, const float* pts, const float* offset, int64_t R,
+                          int32_t S, float* can_pts, float* can_dirs, void* stream);
+/* Its adjoint: g_can_pts / g_can_dirs [R,S,3] (either may be NULL), can_pts = the forward's output ->
+ * g_offset [R,S,3] (required; it is the total dL/d can_pts, i.e. also dL/d offset), g_T [n_verts,4,4], g_verts [n_verts,3]
+ * (overwritten; may be NULL). */
+int nm_human_canonicalize_backward(nm_ctx* ctx, const int32_t* f_id, const double* closest, const float* verts,
+                                   const int32_t* faces, const float* T, const float* pts, const float* can_pts,
+                                   const float* g_can_pts, const float* g_can_dirs, int64_t R, int32_t S,
+                                   int32_t n_verts, float* g_offset, float* g_T, float* g_verts, void* stream);
+/* HumanNeRF.vertex_forward (models/human_nerf.py:92-122) for training: float32 like the reference's torch code, all
+ * parameters on the DEVICE (pose [3J], da_pose [3J], betas [NB], alignment [4,4] row-major = self.alignments[idx]):
+ * T_da2scene [V,4,4] = S . alignment^T . T_t2pose . inv(T_t2da), world_verts [V,3] (may be NULL) = T_da2scene . da-pose
+ * vertices.  Vertices only (the trainer does not use the joint rows). */
+int nm_smpl_scene_forward_train(nm_ctx* ctx, const nm_smpl_model* model, const float* pose, const float* da_pose,
+                                const float* betas, const float* alignment, float scale, float* T_da2scene,
+                                float* world_verts, void* stream);
+/* Its adjoint (what loss.backward() sends to HumanNeRF.poses / betas / alignments, models/human_nerf.py:36-38):
+ * g_T [V,4,4], g_world [V,3] (either may be NULL) -> g_pose [3J], g_betas [NB], g_alignment [4,4] (overwritten). */
+int nm_smpl_scene_backward(nm_ctx* ctx, const nm_smpl_model* model, const float* pose, const float* da_pose,
+                           const float* betas, const float* alignment, float scale, const float* g_T,
+                           const float* g_world, float* g_pose, float* g_betas, float* g_alignment, void* stream);
+
 /* ---- frame drivers: utils/render_utils.py:108-461 ----------------------------------------- */
 typedef struct {
   int32_t samples_per_ray;              /* S */

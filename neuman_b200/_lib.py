@@ -76,6 +76,12 @@ SIGNATURES = {
     "nm_smpl_vertex_transforms": (C.c_int, [_P, C.POINTER(NmSmplModel), _P, _P, _I32, _P, _P, _P]),
     "nm_smpl_scene_transforms": (C.c_int, [_P, C.POINTER(NmSmplModel), _P, _P, _P, C.POINTER(C.c_double), C.c_double,
                                            _P, _P, _P]),
+    "nm_warp_diff_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _P, _P]),
+    "nm_warp_diff_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _P, _I32, _P, _P, _P]),
+    "nm_human_canonicalize": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
+    "nm_human_canonicalize_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P]),
+    "nm_smpl_scene_forward_train": (C.c_int, [_P, C.POINTER(NmSmplModel), _P, _P, _P, _P, _F, _P, _P, _P]),
+    "nm_smpl_scene_backward": (C.c_int, [_P, C.POINTER(NmSmplModel), _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
     "nm_render_vanilla": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(NmCamera), C.POINTER(NmRenderOpts), _I64, _I64, _P,
                                     _P, _P, _I32, _P]),
     "nm_render_smpl_nerf": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(NmCamera), C.POINTER(NmRenderOpts), _I64, _I64, _P,

@@ -262,3 +262,128 @@ def joiner_forward(joiner, input_pts, input_views):
     assert views.shape[0] == pts.shape[0], "input_views must match input_pts"
     params = [p for _, p in joiner.nerf.named_parameters()]
     return _JoinerMLP.apply(pts, views, joiner, *params).reshape(*shape, 4)
+
+
+# ---------------------------------------------------------------------------------------------
+# Human trainer: differentiable observation -> canonical map and SMPL scene transforms (csrc/human_train.cu, smpl.cu)
+# ---------------------------------------------------------------------------------------------
+def _faces_i32(faces, device):
+    f = faces if isinstance(faces, torch.Tensor) else torch.as_tensor(__import__("numpy").asarray(faces))
+    return f[:, :3].to(device=device, dtype=torch.int32).contiguous()
+
+
+class _WarpDiffTinv(torch.autograd.Function):
+    """T_interp_inv of utils/ray_utils.py:72-91 with gradients to the posed vertices and the per-vertex transforms."""
+
+    @staticmethod
+    def forward(fctx, verts, T, f_id, closest, faces):
+        v, t = _f32(verts), _f32(T, verts.device).reshape(-1, 16)
+        ctx = _ctx_for(v)
+        n = int(f_id.shape[0])
+        Tinv = torch.empty(n, 4, 4, device=v.device)
+        with torch.cuda.device(v.device):
+            ctx.check(ctx.lib.nm_warp_diff_forward(ctx.h, _p(f_id), _p(closest), _p(v), _p(faces), _p(t), n, _p(Tinv), ctx.stream()))
+        fctx.save_for_backward(v, t, f_id, closest, faces)
+        fctx.t_shape = tuple(T.shape)
+        return Tinv
+
+    @staticmethod
+    def backward(fctx, g):
+        v, t, f_id, closest, faces = fctx.saved_tensors
+        ctx = _ctx_for(v)
+        need_v, need_t = fctx.needs_input_grad[0], fctx.needs_input_grad[1]
+        g_T = torch.empty_like(t) if need_t else None
+        g_v = torch.empty_like(v) if need_v else None
+        if need_v or need_t:
+            with torch.cuda.device(v.device):
+                ctx.check(ctx.lib.nm_warp_diff_backward(ctx.h, _p(f_id), _p(closest), _p(v), _p(faces), _p(t), int(f_id.shape[0]),
+                                                        _p(_f32(g, v.device)), int(v.shape[0]), _p(g_T), _p(g_v), ctx.stream()))
+        return g_v, (g_T.reshape(fctx.t_shape) if need_t else None), None, None, None
+
+
+def warp_diff_tinv(verts, T, f_id, closest, faces):
+    """verts [V,3], T [V,4,4] CUDA float32 (may require grad); f_id [n] int32, closest [n,3] float64 CUDA (the
+    nm_signed_distance query); faces [F,>=3].  -> T_interp_inv [n,4,4]."""
+    return _WarpDiffTinv.apply(verts, T, f_id.contiguous(), closest.contiguous(), _faces_i32(faces, verts.device))
+
+
+class _HumanCanonicalize(torch.autograd.Function):
+    """trainers/human_nerf_trainer.py:263-276 fused: (can_pts, can_dirs) from the samples, with gradients to the posed
+    vertices, the per-vertex transforms and the offset."""
+
+    @staticmethod
+    def forward(fctx, verts, T, offset, pts, f_id, closest, faces):
+        v, t, p = _f32(verts), _f32(T, verts.device).reshape(-1, 16), _f32(pts, verts.device)
+        off = _f32(offset, v.device) if offset is not None else None
+        ctx = _ctx_for(v)
+        R, S = int(p.shape[0]), int(p.shape[1])
+        cp, cd = torch.empty(R, S, 3, device=v.device), torch.empty(R, S, 3, device=v.device)
+        with torch.cuda.device(v.device):
+            ctx.check(ctx.lib.nm_human_canonicalize(ctx.h, _p(f_id), _p(closest), _p(v), _p(faces), _p(t), _p(p), _p(off), R, S,
+                                                    _p(cp), _p(cd), ctx.stream()))
+        fctx.save_for_backward(v, t, p, cp, f_id, closest, faces)
+        fctx.t_shape = tuple(T.shape)
+        return cp, cd
+
+    @staticmethod
+    def backward(fctx, g_cp, g_cd):
+        v, t, p, cp, f_id, closest, faces = fctx.saved_tensors
+        ctx = _ctx_for(v)
+        need_v, need_t, need_o = fctx.needs_input_grad[:3]
+        R, S = int(p.shape[0]), int(p.shape[1])
+        g_off = torch.empty_like(p)
+        g_T = torch.empty_like(t) if need_t else None
+        g_v = torch.empty_like(v) if need_v else None
+        g_cp = _f32(g_cp, v.device) if g_cp is not None else None
+        g_cd = _f32(g_cd, v.device) if g_cd is not None else None
+        with torch.cuda.device(v.device):
+            ctx.check(ctx.lib.nm_human_canonicalize_backward(ctx.h, _p(f_id), _p(closest), _p(v), _p(faces), _p(t), _p(p), _p(cp),
+                                                             _p(g_cp), _p(g_cd), R, S, int(v.shape[0]), _p(g_off), _p(g_T),
+                                                             _p(g_v), ctx.stream()))
+        return g_v, (g_T.reshape(fctx.t_shape) if need_t else None), (g_off if need_o else None), None, None, None, None
+
+
+def human_canonicalize(pts, verts, T, f_id, closest, faces, offset=None):
+    """pts [R,S,3] (constants), verts [V,3], T [V,4,4], offset [R,S,3] or None (may require grad) -> (can_pts, can_dirs)."""
+    assert pts.dim() == 3 and pts.shape[-1] == 3 and pts.shape[1] >= 2, "pts must be [rays, samples >= 2, 3]"
+    return _HumanCanonicalize.apply(verts, T, offset, pts.detach(), f_id.contiguous(), closest.contiguous(),
+                                    _faces_i32(faces, verts.device))
+
+
+class _VertexForward(torch.autograd.Function):
+    """HumanNeRF.vertex_forward (models/human_nerf.py:92-122) with gradients to pose, betas and alignment."""
+
+    @staticmethod
+    def forward(fctx, pose, betas, alignment, da_pose, model, scale):
+        dev = model.device
+        p, b, a, da = (_f32(x, dev).reshape(-1) for x in (pose, betas, alignment, da_pose))
+        ctx = _ctx_for(p)
+        nv = model.n_verts
+        T, world = torch.empty(nv, 4, 4, device=dev), torch.empty(nv, 3, device=dev)
+        with torch.cuda.device(dev):
+            ctx.check(ctx.lib.nm_smpl_scene_forward_train(ctx.h, C.byref(model.struct), _p(p), _p(da), _p(b), _p(a), float(scale),
+                                                          _p(T), _p(world), ctx.stream()))
+        fctx.save_for_backward(p, b, a, da)
+        fctx.model, fctx.scale = model, float(scale)
+        fctx.shapes = (tuple(pose.shape), tuple(betas.shape), tuple(alignment.shape))
+        return world[None], T[None]
+
+    @staticmethod
+    def backward(fctx, g_world, g_T):
+        p, b, a, da = fctx.saved_tensors
+        model = fctx.model
+        ctx = _ctx_for(p)
+        g_world = _f32(g_world, p.device) if g_world is not None else None
+        g_T = _f32(g_T, p.device) if g_T is not None else None
+        gp, gb, ga = torch.empty_like(p), torch.empty_like(b), torch.empty_like(a)
+        with torch.cuda.device(p.device):
+            ctx.check(ctx.lib.nm_smpl_scene_backward(ctx.h, C.byref(model.struct), _p(p), _p(da), _p(b), _p(a), fctx.scale, _p(g_T),
+                                                     _p(g_world), _p(gp), _p(gb), _p(ga), ctx.stream()))
+        sp, sb, sa = fctx.shapes
+        return gp.reshape(sp), gb.reshape(sb), ga.reshape(sa), None, None, None
+
+
+def vertex_forward(model, pose, betas, alignment, scale, da_pose):
+    """model: ops.SmplModelDevice; pose [1,3J], betas [1,NB], alignment [4,4] (self.alignments[idx]), da_pose [1,3J] CUDA
+    tensors -> (world_verts [1,V,3], T_da2scene [1,V,4,4]) float32 with gradients to pose / betas / alignment."""
+    return _VertexForward.apply(pose, betas, alignment, da_pose, model, scale)

@@ -24,6 +24,7 @@ SOURCES = {           # file -> extra flags
     "render.cu": ["-fmad=false"],
     "warp.cu": [],
     "smpl.cu": [],
+    "human_train.cu": [],
     "mlp_simt.cu": [],
     "mlp_tc.cu": [],
     "mlp_tc_bwd.cu": [],

@@ -11,6 +11,7 @@
 // Pose blend shapes are computed by the reference but NOT applied (v_posed = v_shaped, models/smpl.py:334),
 // so they are not evaluated here.
 #include "nm_internal.cuh"
+#include "smpl_train_kernels.cuh"
 
 #define SMPL_MAX_J 64
 
@@ -242,6 +243,93 @@ extern "C" int nm_smpl_scene_transforms(nm_ctx* ctx, const nm_smpl_model* m, con
   for (int a = 0; a < 4; ++a)
     for (int b = 0; b < 4; ++b) pre.v[4 * a + b] = alignment[4 * b + a] * (a < 3 ? scale : 1.0);
   k_smpl_scene<<<(total + 127) / 128, 128, 0, st>>>(T_pose, T_da, rest, pre, total, T_da2scene, world_verts);
+  NM_CHECK_LAUNCH(ctx);
+  return NM_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// Training-time scene transforms and their adjoint (smpl_train_kernels.cuh): HumanNeRF.vertex_forward
+// (models/human_nerf.py:92-122) in float32 with the alignment read from DEVICE memory (it is an nn.Parameter the
+// trainer optimises: no host round trip per step), and what loss.backward() sends to poses / betas / alignments.
+// --------------------------------------------------------------------------------------------------
+struct SmplTrainWs {
+  float *v_shaped, *J, *A, *T_pose, *T_da, *gP, *gD, *grest, *gA_pose, *gA_da, *gJ, *gpre;
+};
+
+static int smpl_train_workspace(nm_ctx* ctx, int nv, int nj, bool backward, SmplTrainWs& w) {
+  auto pad64 = [](size_t n) { return (n + 63) & ~size_t(63); };
+  size_t floats = pad64((size_t)nv * 3) + pad64((size_t)nj * 3) + pad64((size_t)nj * 16) + 2 * pad64((size_t)nv * 16);
+  if (backward) floats += 2 * pad64((size_t)nv * 16) + pad64((size_t)nv * 3) + 2 * pad64((size_t)nj * 16) + pad64((size_t)nj * 3) + 64;
+  char* ws;
+  int rc;
+  if ((rc = nm_impl_workspace(ctx, floats * sizeof(float), &ws))) return rc;
+  float* p = reinterpret_cast<float*>(ws);
+  auto take = [&](size_t n) { float* r = p; p += pad64(n); return r; };
+  w.v_shaped = take((size_t)nv * 3); w.J = take((size_t)nj * 3); w.A = take((size_t)nj * 16);
+  w.T_pose = take((size_t)nv * 16); w.T_da = take((size_t)nv * 16);
+  if (backward) {
+    w.gP = take((size_t)nv * 16); w.gD = take((size_t)nv * 16); w.grest = take((size_t)nv * 3);
+    w.gA_pose = take((size_t)nj * 16); w.gA_da = take((size_t)nj * 16); w.gJ = take((size_t)nj * 3); w.gpre = take(64);
+  }
+  if ((size_t)(reinterpret_cast<char*>(p) - ws) > ctx->ws_bytes)
+    NM_FAIL(ctx, NM_ERR_STATE, "nm_smpl_scene_*_train: workspace overflow (internal sizing bug)");
+  return NM_OK;
+}
+
+extern "C" int nm_smpl_scene_forward_train(nm_ctx* ctx, const nm_smpl_model* m, const float* pose, const float* da_pose,
+                                           const float* betas, const float* alignment, float scale, float* T_da2scene,
+                                           float* world_verts, void* stream) {
+  NM_ENTER(ctx);
+  int rc = check_model(ctx, m);
+  if (rc) return rc;
+  if (!pose || !da_pose || !betas || !alignment || !T_da2scene)
+    NM_FAIL(ctx, NM_ERR_INVALID, "nm_smpl_scene_forward_train: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nv = m->n_verts, nj = m->n_joints;
+  SmplTrainWs w{};
+  if ((rc = smpl_train_workspace(ctx, nv, nj, false, w))) return rc;
+  if ((rc = smpl_lbs(ctx, m, pose, betas, 0, w.v_shaped, w.J, w.A, w.T_pose, nullptr, st))) return rc;
+  if ((rc = smpl_lbs(ctx, m, da_pose, betas, 0, w.v_shaped, w.J, w.A, w.T_da, nullptr, st))) return rc;
+  k_smplt_scene_forward<<<(nv + 127) / 128, 128, 0, st>>>(w.T_pose, w.T_da, w.v_shaped, alignment, scale, nv, T_da2scene,
+                                                          world_verts);
+  NM_CHECK_LAUNCH(ctx);
+  return NM_OK;
+}
+
+extern "C" int nm_smpl_scene_backward(nm_ctx* ctx, const nm_smpl_model* m, const float* pose, const float* da_pose,
+                                      const float* betas, const float* alignment, float scale, const float* g_T,
+                                      const float* g_world, float* g_pose, float* g_betas, float* g_alignment,
+                                      void* stream) {
+  NM_ENTER(ctx);
+  int rc = check_model(ctx, m);
+  if (rc) return rc;
+  if (!pose || !da_pose || !betas || !alignment || (!g_T && !g_world) || !g_pose || !g_betas || !g_alignment)
+    NM_FAIL(ctx, NM_ERR_INVALID, "nm_smpl_scene_backward: null argument");
+  if (m->n_joints > SMPLT_MAX_J) NM_FAIL(ctx, NM_ERR_INVALID, "nm_smpl_scene_backward: too many joints");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nv = m->n_verts, nj = m->n_joints, nb = m->n_betas;
+  SmplTrainWs w{};
+  if ((rc = smpl_train_workspace(ctx, nv, nj, true, w))) return rc;
+  // forward intermediates (the LBS of both poses is ~10 us; recomputing it beats keeping 2 x 441 KB alive per step)
+  if ((rc = smpl_lbs(ctx, m, pose, betas, 0, w.v_shaped, w.J, w.A, w.T_pose, nullptr, st))) return rc;
+  if ((rc = smpl_lbs(ctx, m, da_pose, betas, 0, w.v_shaped, w.J, w.A, w.T_da, nullptr, st))) return rc;
+  NM_CHECK_CUDA(ctx, cudaMemsetAsync(w.gA_pose, 0, (size_t)(w.gpre + 64 - w.gA_pose) * sizeof(float), st));   // gA_pose, gA_da, gJ, gpre
+  NM_CHECK_CUDA(ctx, cudaMemsetAsync(g_betas, 0, (size_t)nb * sizeof(float), st));
+  const int chunks = (nv + SMPLT_VPT - 1) / SMPLT_VPT;
+  k_smplt_scene_backward<<<(chunks + 63) / 64, 64, 0, st>>>(w.T_pose, w.T_da, w.v_shaped, alignment, scale, g_T, g_world, nv,
+                                                            w.gP, w.gD, w.grest, w.gpre);
+  NM_CHECK_LAUNCH(ctx);
+  k_smplt_blend_backward<<<(nv + 127) / 128, 128, 0, st>>>(m->weights, w.gP, w.gD, nv, nj, w.gA_pose, w.gA_da);
+  NM_CHECK_LAUNCH(ctx);
+  SmpltParents par;
+  for (int j = 0; j < nj; ++j) par.p[j] = m->parents[j];
+  k_smplt_chain_backward<<<1, 32, 0, st>>>(pose, da_pose, w.J, par, nj, w.gA_pose, w.gA_da, w.gpre, scale, g_pose, w.gJ,
+                                           g_alignment);
+  NM_CHECK_LAUNCH(ctx);
+  k_smplt_vshaped_backward<<<(nv + 127) / 128, 128, 0, st>>>(m->J_regressor, w.gJ, nv, nj, w.grest);
+  NM_CHECK_LAUNCH(ctx);
+  const int n3 = nv * 3;
+  k_smplt_betas_backward<<<((n3 + 63) / 64 + 63) / 64, 64, 0, st>>>(m->shapedirs, w.grest, n3, nb, g_betas);
   NM_CHECK_LAUNCH(ctx);
   return NM_OK;
 }

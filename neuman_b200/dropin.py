@@ -55,7 +55,9 @@ def install(reference_root=None, train=False):
     """train=True additionally routes the trainers' autograd path to the CUDA training kernels: Joiner.forward of
     8x256 nets (gradients to the parameters and to input_pts / input_views, which is what
     trainers/human_nerf_trainer.py:241-278 differentiates through) and raw2outputs with respect to `raw`
-    (trainers/vanilla_nerf_trainer.py:45-96), and the human trainer's libigl queries to the device BVH."""
+    (trainers/vanilla_nerf_trainer.py:45-96), the human trainer's libigl queries to the device BVH, its differentiable
+    warp (`warp_samples_to_canonical_diff`, utils/ray_utils.py:69-93) and `HumanNeRF.vertex_forward`
+    (models/human_nerf.py:92-122) to the forward / adjoint kernels of csrc/human_train.cu and csrc/smpl.cu."""
     if reference_root and reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     from . import autograd, ops, render
@@ -194,16 +196,41 @@ def install(reference_root=None, train=False):
             pass
     else:
         ry.warp_samples_to_canonical_diff = ref_diff
-    return {"render_utils": ru, "ray_utils": ry, "vanilla": mv}
+
+    # ---- HumanNeRF.vertex_forward (models/human_nerf.py:92-122): the per-step SMPL transforms of the human trainer ----
+    hn = importlib.import_module("models.human_nerf")
+    ref_vf = _originals(hn.HumanNeRF, ("vertex_forward",))["vertex_forward"]
+    if train:
+        def vertex_forward(self, idx, pose=None, beta=None):
+            bm = getattr(self, "body_model", None)
+            try:
+                ok = bm is not None and bm.v_template.is_cuda and self.poses.is_cuda and self.da_smpl.is_cuda
+            except AttributeError:
+                ok = False
+            if not ok:
+                return ref_vf(self, idx, pose, beta)
+            dm = getattr(bm, "_nm_device_model", None)
+            if dm is None:
+                n_betas = int(self.betas.shape[-1])
+                dm = ops.SmplModelDevice(bm.v_template, bm.shapedirs[:, :, :n_betas], bm.J_regressor, bm.lbs_weights, bm.parents,
+                                         device=bm.v_template.device)
+                bm._nm_device_model = dm
+            pose = self.poses[idx][None] if pose is None else pose
+            beta = self.betas[idx][None] if beta is None else beta
+            return autograd.vertex_forward(dm, pose, beta, self.alignments[idx], float(self.scale), self.da_smpl)
+        hn.HumanNeRF.vertex_forward = vertex_forward
+    else:
+        hn.HumanNeRF.vertex_forward = ref_vf
+    return {"render_utils": ru, "ray_utils": ry, "vanilla": mv, "human_nerf": hn}
 
 
 def uninstall():
     """Puts the reference's own functions back (tests)."""
-    for name in ("utils.render_utils", "utils.ray_utils", "models.vanilla", "igl"):
+    for name in ("utils.render_utils", "utils.ray_utils", "models.vanilla", "models.human_nerf", "igl"):
         mod = sys.modules.get(name)
         if mod is None:
             continue
-        targets = [mod] + ([mod.Joiner] if name == "models.vanilla" else [])
+        targets = [mod] + ([mod.Joiner] if name == "models.vanilla" else []) + ([mod.HumanNeRF] if name == "models.human_nerf" else [])
         for t in targets:
             for k, v in t.__dict__.get(_ORIG, {}).items():
                 setattr(t, k, v)

@@ -105,17 +105,47 @@ def build_nerf(opt):
 
 
 class OffsetNet(nn.Module):
-    """models/vanilla.py:169-177: parameter container of one offset network (Embedder over (x, y, z, t) + an 8x256 NeRF trunk
-    with `output_linear` [3,256] and output scaling), so that `hybrid_model_state_dict` checkpoints load unchanged.  It is
-    a training-time network (trainers/human_nerf_trainer.py:241-278); the renderers never evaluate it and
-    no kernel is built for it: forward raises."""
+    """models/vanilla.py:169-177: one offset network (Embedder over (x, y, z, t) + an 8x256 NeRF trunk with
+    `output_linear` [3,256] and output scaling); parameter names and shapes are the reference's, so
+    `hybrid_model_state_dict` checkpoints load unchanged.  It is a training-time network
+    (trainers/human_nerf_trainer.py:259-261); the renderers never evaluate it.
+
+    No hand-written kernel exists for it yet: `forward` evaluates it with library GEMMs (torch.nn.functional.linear ->
+    cuBLAS, float32) so that the human trainer's step runs end to end; DESIGN.md §9 lists it as the next kernel."""
 
     def __init__(self, pos_pe, nerf):
         super().__init__()
         self.pos_pe, self.nerf = pos_pe, nerf
 
+    def encode(self, x):
+        """Embedder.forward, mapping 'posenc' (models/vanilla.py:60-79,90-92): [x, sin(f0 x), cos(f0 x), sin(f1 x), ...]."""
+        pe = self.pos_pe
+        if pe.mapping != 'posenc':
+            raise NotImplementedError("offset nets use the 'posenc' mapping (models/vanilla.py:180-188)")
+        freqs = 2.0 ** torch.linspace(pe.min_freq, pe.max_freq, steps=pe.N_freqs, device=x.device)
+        out = [x]
+        for f in freqs:
+            out += [torch.sin(x * f), torch.cos(x * f)]
+        return torch.cat(out, -1)
+
     def forward(self, input_pts, cur_iter=None):
-        raise NotImplementedError("OffsetNet is training-only (trainers/human_nerf_trainer.py:241-278); its kernels are not built")
+        assert cur_iter is None                                          # (:91)
+        import torch.nn.functional as F
+        n = self.nerf
+        e = self.encode(input_pts)
+        h = e
+        for i, lin in enumerate(n.pts_linears):                         # NeRF.forward, use_viewdirs=False (:127-152)
+            h = F.relu(lin(h))
+            if i in n.skips:
+                h = torch.cat([e, h], -1)
+        out = n.output_linear(h)
+        if n.scale_type == 'no':
+            return out
+        if n.scale_type == 'linear':
+            return out * n.scale
+        if n.scale_type == 'tanh':
+            return torch.tanh(out) * n.scale
+        raise ValueError(n.scale_type)
 
 
 def build_offset_net(opt):
@@ -203,17 +233,20 @@ class HumanNeRF(nn.Module):
                 self.body_model = SMPL(smpl_model, device="cuda")
 
     def vertex_forward(self, idx, pose=None, beta=None):
-        """models/human_nerf.py:92-122 -> (world_verts [1,V,3] f32, T_da2scene [1,V,4,4] f32) on the device: one
-        nm_smpl_scene_transforms call (LBS of the frame pose and of the 'da' pose, T_t2pose . inv(T_t2da), alignment^T and
-        the scene scale; float64 inside like data_io/neuman_helper.py:299-330, returned in the reference's float32).
-        Inference only: the SMPL / warp adjoints the human trainer differentiates through are not built."""
+        """models/human_nerf.py:92-122 -> (world_verts [1,V,3] f32, T_da2scene [1,V,4,4] f32) on the device.
+        Without autograd: one nm_smpl_scene_transforms call (LBS of the frame pose and of the 'da' pose,
+        T_t2pose . inv(T_t2da), alignment^T and the scene scale; float64 inside like data_io/neuman_helper.py:299-330,
+        returned in the reference's float32).  Under autograd (the human trainer optimises poses / betas / alignments,
+        trainers/human_nerf_trainer.py:263): the float32 training kernels, whose adjoint returns the gradients of those
+        three parameters (neuman_b200.autograd.vertex_forward)."""
         if self.body_model is None:
             raise RuntimeError("HumanNeRF was built without an SMPL model (pass smpl_model=...)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in (self.poses, self.betas, self.alignments)):
-            raise NotImplementedError("vertex_forward under autograd (SMPL adjoint) is not built; wrap the call in torch.no_grad()")
         pose = self.poses[idx][None] if pose is None else pose
         beta = self.betas[idx][None] if beta is None else beta
         m = self.body_model.dev_model
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (pose, beta, self.alignments)):
+            from . import autograd
+            return autograd.vertex_forward(m, pose, beta, self.alignments[idx], float(self.scale), self.da_smpl)
         world, _, T = ops.smpl_scene_transforms(m, pose.detach(), beta.detach(), self.alignments[idx].detach().cpu().numpy(),
                                                 float(self.scale))
         return world[None], T[:m.n_verts].float()[None]

@@ -380,23 +380,27 @@ def signed_distance(pts, verts, faces, actor=NM_MAX_ACTORS - 1, device=None):
 
 def warp_samples_to_canonical_diff(pts, verts, faces, T, actor=NM_MAX_ACTORS - 1):
     """utils/ray_utils.py:69-93: the closest-face query (igl.signed_distance on the CPU in the reference, :70) runs on
-    the device; the differentiable part -- barycentric coordinates of the closest point from cross products (:72-88),
-    blend of the three per-vertex transforms and its inverse (:90-91) -- is the same torch algebra, so gradients reach
-    `verts` and `T` through autograd exactly as in the reference.  pts: [n,3] numpy or tensor (treated as constants);
-    verts [V,3], T [V,4,4]: CUDA tensors.  Returns (T_interp_inv [n,4,4], f_id [n], signed_dist [n])."""
+    the device BVH; the differentiable part -- barycentric coordinates of the closest point from cross products (:72-88),
+    blend of the three per-vertex transforms and its inverse (:90-91) -- is one kernel (nm_warp_diff_forward) whose
+    adjoint (nm_warp_diff_backward) sends gradients to `verts` and `T` as torch autograd does in the reference.
+    pts: [n,3] numpy or tensor (treated as constants); verts [V,3], T [V,4,4]: CUDA tensors.
+    Returns (T_interp_inv [n,4,4], f_id [n], signed_dist [n])."""
+    from . import autograd
     signed_dist, f_id, closest = signed_distance(torch.as_tensor(np.asarray(pts)) if not isinstance(pts, torch.Tensor) else pts.detach(),
                                                  verts, faces, actor=actor, device=verts.device)
-    fa = (faces if isinstance(faces, torch.Tensor) else torch.as_tensor(np.asarray(faces)))[:, :3].to(verts.device).long()
-    tri = verts[fa[f_id.long()]]                                        # [n,3,3]
-    closest = closest.float()
-    a, b, c = tri[:, 0], tri[:, 1], tri[:, 2]
-    nrm = torch.cross(b - a, c - a, dim=-1)
-    denom = (nrm * nrm).sum(-1)
-    u = (nrm * torch.cross(c - b, closest - b, dim=-1)).sum(-1) / denom
-    v = (nrm * torch.cross(a - c, closest - c, dim=-1)).sum(-1) / denom
-    bary = torch.stack([u, v, 1 - u - v], dim=1)
-    T_interp = (T[fa[f_id.long()]] * bary[..., None, None]).sum(dim=1)
-    return torch.inverse(T_interp), f_id, signed_dist
+    return autograd.warp_diff_tinv(verts, T, f_id, closest, faces), f_id, signed_dist
+
+
+def eval_human_samples(pts, verts, faces, T, offset=None, actor=NM_MAX_ACTORS - 1):
+    """The geometric part of HumanNeRFTrainer._eval_human_samples (trainers/human_nerf_trainer.py:263-276): samples
+    pts [R,S,3] of the observation space -> canonical points (inverse blended transform, + offset) and canonical
+    directions, fused (nm_human_canonicalize) and differentiable with respect to verts [V,3], T [V,4,4] and offset [R,S,3].
+    Returns (can_pts, can_dirs, f_id [R*S], signed_dist [R*S])."""
+    from . import autograd
+    p = _f32(pts, verts.device)
+    signed_dist, f_id, closest = signed_distance(p.detach().reshape(-1, 3), verts, faces, actor=actor, device=verts.device)
+    cp, cd = autograd.human_canonicalize(p, verts, T, f_id, closest, faces, offset)
+    return cp, cd, f_id, signed_dist
 
 
 def warp_samples_to_canonical(pts, verts, faces, T, actor=0, return_face_id=False):

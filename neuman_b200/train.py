@@ -104,3 +104,33 @@ def train_batch(coarse_net, fine_net, optimizer, batch, opt, iteration=0, nan_gu
                 g.masked_fill_(bad, 0.0)
     optimizer.step()
     return total.detach()
+
+
+def eval_human_samples(net, batch, opt, faces, offset_net=None, t_rand=None, actor=ops.NM_MAX_ACTORS - 1):
+    """HumanNeRFTrainer._eval_human_samples (trainers/human_nerf_trainer.py:241-278) on the CUDA path.
+
+    net: neuman_b200.HumanNeRF built with per-frame SMPL parameters and a body model; batch: a HumanRayBatcher /
+    HumanRayDataset batch (origin, direction, human_near, human_far, cur_view_f, cap_id); faces: the SMPL faces [F,3]
+    (the reference reads them from the capture's posed mesh, :268); offset_net: one of net.offset_nets (the reference draws
+    `random.choice(self.net.offset_nets)`, :261) or None to skip the offset.
+
+    Stages: ray_to_samples kernel (:248-257) -> offset network (:260-261; library GEMMs for now) -> vertex_forward
+    training kernels (:264) -> closest-face query on the device BVH + fused blend / inverse / apply / offset / directions
+    (:265-276, nm_signed_distance + nm_human_canonicalize) -> canonical human network on the tensor-core training kernel
+    (:277).  loss.backward() then runs the adjoint kernels of every stage: gradients reach the human network, the offset
+    network, and net.poses / net.betas / net.alignments.
+    Returns the reference's tuple (human_pts [R*S,3], human_dirs, human_z_vals, can_pts, can_dirs, human_out)."""
+    dev = next(net.coarse_human_net.parameters()).device
+    human_batch = {'origin': batch['origin'].to(dev), 'direction': batch['direction'].to(dev),
+                   'near': batch['human_near'].to(dev), 'far': batch['human_far'].to(dev)}
+    human_pts, human_dirs, human_z_vals = ops.ray_to_samples(human_batch, opt.samples_per_ray, perturb=getattr(opt, 'perturb', 0.),
+                                                             device=dev, t_rand=t_rand)
+    human_b, human_n, _ = human_pts.shape
+    offset = None
+    if offset_net is not None:
+        cur_time = torch.ones_like(human_pts[..., 0:1]) * float(batch['cur_view_f'])
+        offset = offset_net(torch.cat([human_pts, cur_time], dim=-1))
+    mesh, raw_Ts = net.vertex_forward(int(batch['cap_id']))
+    can_pts, can_dirs, _, _ = ops.eval_human_samples(human_pts, mesh[0], faces, raw_Ts[0], offset=offset, actor=actor)
+    human_out = net.coarse_human_net(can_pts, can_dirs)
+    return human_pts.reshape(-1, 3), human_dirs, human_z_vals, can_pts, can_dirs, human_out

@@ -54,7 +54,11 @@ class _Anything:
 def _stub(name, **attrs):
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
-    m.__getattr__ = lambda attr: _Anything  # module-level fallback (PEP 562)
+    def fallback(attr):                      # module-level fallback (PEP 562); dunders stay missing (inspect probes __file__)
+        if attr.startswith("__"):
+            raise AttributeError(attr)
+        return _Anything
+    m.__getattr__ = fallback
     sys.modules[name] = m
     return m
 

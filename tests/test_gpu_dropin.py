@@ -155,3 +155,92 @@ def test_reference_stage_functions_and_forward_on_cuda(ref):
     # under autograd (training) the reference's torch path runs unless install(train=True)
     out = coarse(torch.from_numpy(g["n_pts"]).to(dev), torch.from_numpy(g["n_views"]).to(dev))
     assert out.requires_grad
+
+
+def _reference_human_trainer_case(ref, device):
+    """The reference's HumanNeRF with per-frame SMPL parameters, assembled as models/human_nerf.py:31-90 does (the SMPL
+    pickle path is hard-coded there to <repo>/data/smplx/smpl, licence-gated and absent: the attributes are set here from a
+    synthetic SMPL-shaped pickle instead), a ray batch through the body, and a stand-in for the trainer object holding the
+    three members HumanNeRFTrainer._eval_human_samples reads (opt, net, val_dataset.scene.captures[i].posed_mesh_cpu)."""
+    import os
+    import tempfile
+    import types
+    from oracle import synth_smpl
+    torch.manual_seed(1)
+    opt = ref_opts.default_opt(num_offset_nets=1, use_cuda=(device == "cuda"), offset_scale=0.02, offset_scale_type="tanh",
+                               samples_per_ray=24, perturb=0.0)
+    net = quiet(ref.human_nerf.HumanNeRF, opt)
+    rng = np.random.RandomState(6)
+    pose, betas = rng.normal(0, 0.3, (1, 72)).astype(np.float32), rng.normal(0, 1, (1, 10)).astype(np.float32)
+    ang = 0.2
+    align = np.eye(4, dtype=np.float32)
+    align[:3, :3] = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    align = align.T.copy()
+    align[3, :3] = (0.3, -0.1, 2.0)
+    P = torch.nn.Parameter
+    net.poses, net.betas = P(torch.from_numpy(pose).to(device)), P(torch.from_numpy(betas).to(device))
+    net.alignments, net.scale = P(torch.from_numpy(align[None]).to(device)), 0.4
+    pk = os.path.join(tempfile.mkdtemp(), "SMPL_NEUTRAL.pkl")
+    synth_smpl.write_pickle(pk, 0)
+    net.body_model = ref.smpl.SMPL(pk, gender="neutral", device=torch.device(device))
+    da = torch.zeros(24, 3)
+    da[1, 2], da[2, 2] = 1.0, -1.0
+    net.da_smpl = P(da.reshape(1, -1).to(device), requires_grad=False)
+    faces = net.body_model.faces_tensor.cpu()
+    cap = types.SimpleNamespace(posed_mesh_cpu=types.SimpleNamespace(faces_packed=lambda: faces))
+    me = types.SimpleNamespace(opt=opt, net=net, val_dataset=types.SimpleNamespace(scene=types.SimpleNamespace(captures=[cap])))
+    return me, net
+
+
+def test_reference_human_trainer_step_runs_on_the_cuda_path(ref):
+    """install(train=True) under the reference's own HumanNeRFTrainer._eval_human_samples
+    (trainers/human_nerf_trainer.py:241-278) and loss.backward(): ray_to_samples, vertex_forward (SMPL training kernels),
+    warp_samples_to_canonical_diff (device BVH query + blend/inverse kernel), Joiner.forward (tensor-core training kernel) and
+    their adjoints, against the SAME method of the unpatched reference on the CPU."""
+    import importlib
+    tr = importlib.import_module("trainers.human_nerf_trainer")
+    from neuman_b200 import dropin
+    dropin.uninstall()
+    try:
+        me_c, net_c = _reference_human_trainer_case(ref, "cpu")
+        with torch.no_grad():
+            V0 = net_c.vertex_forward(0)[0][0].numpy()
+        rng = np.random.RandomState(3)
+        R = 64
+        eye = V0.mean(0) + np.array([0.0, 0.0, -2.0])
+        d = V0[rng.randint(0, V0.shape[0], R)] + rng.normal(0, 0.01, (R, 3)) - eye
+        dist = np.linalg.norm(d, axis=1, keepdims=True)
+        mk = lambda dev: {"origin": torch.from_numpy(np.repeat(eye[None], R, 0)).float().to(dev),
+                          "direction": torch.from_numpy((d / dist).astype(np.float32)).to(dev),
+                          "human_near": torch.from_numpy(dist - 0.15).float().to(dev),
+                          "human_far": torch.from_numpy(dist + 0.15).float().to(dev), "cur_view_f": torch.tensor(3 / 11), "cap_id": 0}
+        w = torch.from_numpy(rng.normal(0, 1, (R, 24, 3)).astype(np.float32))
+        out_c = quiet(tr.HumanNeRFTrainer._eval_human_samples, me_c, mk("cpu"), "cpu")
+        ((out_c[3] * w).sum() + (out_c[4] * w.flip(0)).sum()).backward()
+        # ---- the same call with the CUDA path installed ----
+        nb.install(ref_import.REF_ROOT, train=True)
+        me_g, net_g = _reference_human_trainer_case(ref, "cuda")
+        net_g.load_state_dict(net_c.state_dict())
+        l0 = launches()
+        out_g = quiet(tr.HumanNeRFTrainer._eval_human_samples, me_g, mk("cuda"), "cuda")
+        ((out_g[3] * w.cuda()).sum() + (out_g[4] * w.flip(0).cuda()).sum()).backward()
+        assert launches() - l0 >= 12, "the reference's trainer step did not reach libneuman_b200"
+        assert all(o.is_cuda for o in out_g)
+        assert np.abs(out_g[0].detach().cpu().numpy() - out_c[0].detach().numpy()).max() < 2e-6          # human_pts
+        e = np.abs(out_g[3].detach().cpu().numpy() - out_c[3].detach().numpy()).max(-1)                   # can_pts
+        assert (e > 5e-6).mean() < 0.005, ((e > 5e-6).mean(), e.max())      # medial-axis ties of the fp32 arg-min aside
+        ok = e <= 5e-6
+        assert np.abs(out_g[5].detach().cpu().numpy() - out_c[5].detach().numpy())[ok].max() < 2e-3      # human_out (11-bit operands)
+        for name in ("poses", "betas", "alignments"):
+            g, c = getattr(net_g, name).grad.cpu().numpy(), getattr(net_c, name).grad.numpy()
+            assert np.isfinite(g).all() and np.abs(g - c).max() < 2e-2 * (1 + np.abs(c).max()), (name, np.abs(g - c).max(), np.abs(c).max())
+        g, c = net_g.offset_nets[0].nerf.output_linear.weight.grad.cpu().numpy(), net_c.offset_nets[0].nerf.output_linear.weight.grad.numpy()
+        assert np.abs(g - c).max() < 2e-2 * (1 + np.abs(c).max())
+        # the human network's own gradients come from a second loss through its output
+        net_g.zero_grad()
+        out_g = quiet(tr.HumanNeRFTrainer._eval_human_samples, me_g, mk("cuda"), "cuda")
+        out_g[5].square().mean().backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net_g.coarse_human_net.parameters())
+        assert net_g.poses.grad is not None and torch.isfinite(net_g.poses.grad).all()
+    finally:
+        nb.install(ref_import.REF_ROOT)             # back to the module fixture's state (inference drop-in)

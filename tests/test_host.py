@@ -47,6 +47,29 @@ def test_state_dict_keys_equal_reference():
     pc.load_state_dict(rc.state_dict())                              # checkpoints load unchanged
 
 
+@pytest.mark.reference
+@pytest.mark.parametrize("scale_type", ["linear", "tanh", "no"])
+def test_offset_net_equals_reference(scale_type):
+    """neuman_b200.OffsetNet (library-GEMM forward, models/vanilla.py:169-205) against the reference's OffsetNet with the
+    same seeded weights: bit-equal on the CPU, gradients included."""
+    from oracle import ref_import
+    ref = ref_import.load()
+    opt = nb.default_opt(use_cuda=False, num_offset_nets=1, offset_scale=0.7, offset_scale_type=scale_type)
+    torch.manual_seed(3)
+    mine = nb.build_offset_net(opt)
+    torch.manual_seed(3)
+    theirs = ref.vanilla.build_offset_net(opt)
+    assert list(mine.state_dict()) == list(theirs.state_dict())
+    theirs.load_state_dict(mine.state_dict())
+    x = torch.randn(40, 6, 4)
+    a, b = mine(x), theirs(x)
+    assert a.shape == (40, 6, 3) and torch.equal(a, b)
+    a.square().sum().backward()
+    b.square().sum().backward()
+    for (k, p), q in zip(mine.named_parameters(), theirs.parameters()):
+        assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-7), k
+
+
 def test_shard_ranges_cover_every_pixel_once():
     for n, world in ((921600, 8), (4096, 3), (10, 4), (7, 8), (0, 2)):
         seen = np.zeros(n, dtype=np.int32)
