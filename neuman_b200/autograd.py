@@ -97,6 +97,7 @@ class _JoinerMLP(torch.autograd.Function):
                                                    _p(sm), ctx.stream()))
         fctx.joiner = joiner
         fctx.stash = (sx, sf, sv, sm)
+        fctx.param_versions = tuple(p._version for _, p in joiner.nerf.named_parameters())
         fctx.save_for_backward(pts, views, *params)
         return raw
 
@@ -108,6 +109,14 @@ class _JoinerMLP(torch.autograd.Function):
         names = [k for k, _ in joiner.nerf.named_parameters()]
         pts, views = fctx.saved_tensors[:2]
         P = dict(zip(names, fctx.saved_tensors[2:]))
+        # `params` may be tensors COMPUTED for a carrier module (models.offset_forward_at_time) rather than the module's own
+        # parameters: if the carrier was re-loaded since this forward, put the values of this forward back before the chain
+        mod_params = [p for _, p in joiner.nerf.named_parameters()]
+        if (any(p._version != v for p, v in zip(mod_params, fctx.param_versions))
+                and any(P[k] is not p for k, p in zip(names, mod_params))):
+            with torch.no_grad():
+                for k, p in zip(names, mod_params):
+                    p.copy_(P[k])
         g = g_raw.reshape(-1, 4).float().contiguous()
         need_w = any(fctx.needs_input_grad[3:])
         d_pts = d_views = None

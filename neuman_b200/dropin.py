@@ -89,6 +89,18 @@ def install(reference_root=None, train=False):
         return ref_forward(self, input_pts, input_views)          # other training / CPU / other architectures
     mv.Joiner.forward = joiner_forward
 
+    # ---- offset networks (models/vanilla.py:169-177): a Joiner on the tensor-core kernels when the time column is constant ----
+    ref_off_forward = _originals(mv.OffsetNet, ("forward",))["forward"]
+
+    def offset_forward(self, input_pts, cur_iter=None):
+        if cur_iter is None and on_cuda(input_pts) and (train or not torch.is_grad_enabled()):
+            from . import models
+            out = models.offset_forward_tc_if_constant_time(self, input_pts)
+            if out is not None:
+                return out
+        return ref_off_forward(self, input_pts, cur_iter)
+    mv.OffsetNet.forward = offset_forward
+
     # ---- composite (utils/render_utils.py:69-105) ----
     ref_raw2outputs = o_ru["raw2outputs"]
 
@@ -230,7 +242,7 @@ def uninstall():
         mod = sys.modules.get(name)
         if mod is None:
             continue
-        targets = [mod] + ([mod.Joiner] if name == "models.vanilla" else []) + ([mod.HumanNeRF] if name == "models.human_nerf" else [])
+        targets = [mod] + ([mod.Joiner, mod.OffsetNet] if name == "models.vanilla" else []) + ([mod.HumanNeRF] if name == "models.human_nerf" else [])
         for t in targets:
             for k, v in t.__dict__.get(_ORIG, {}).items():
                 setattr(t, k, v)

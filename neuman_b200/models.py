@@ -110,26 +110,33 @@ class OffsetNet(nn.Module):
     `hybrid_model_state_dict` checkpoints load unchanged.  It is a training-time network
     (trainers/human_nerf_trainer.py:259-261); the renderers never evaluate it.
 
-    No hand-written kernel exists for it yet: `forward` evaluates it with library GEMMs (torch.nn.functional.linear ->
-    cuBLAS, float32) so that the human trainer's step runs end to end; DESIGN.md §9 lists it as the next kernel."""
+    Tensor-core path.  Inside one training step the time input is ONE number for the whole batch (`cur_view_f`, :260), and
+    the trunk is the Joiner's trunk.  For a fixed t the network is therefore exactly a Joiner on (x, y, z):
+      * the 21 time channels of the 84-channel encoding are constants: their products with the layer-0 / skip-layer
+        weight columns fold into those layers' biases, the 63 spatial channels are the Joiner's position encoding;
+      * `output_linear` (3 x 256, any sign) is carried through the Joiner's non-negative head as y = relu(y) - relu(-y):
+        feature rows 0..2 = +W_o, 3..5 = -W_o, a unit views layer, rgb = [I, -I].
+    `forward_at_time` builds those weights with differentiable torch indexing (a few 256-wide tensors), runs the SAME
+    tcgen05 training / inference kernels as every other network (k_mlp_tc, k_mlp_tc_bwd, k_dw_gemm), and autograd carries
+    the Joiner-shaped gradients back to this module's parameters.  `forward` uses it when the time column is constant and
+    the architecture is the reference's default (8 x 256, skip 4, 10 log-spaced frequencies); otherwise it evaluates the
+    network with library GEMMs (torch.nn.functional.linear, float32), which is also the CPU path."""
 
     def __init__(self, pos_pe, nerf):
         super().__init__()
         self.pos_pe, self.nerf = pos_pe, nerf
 
+    # ---- library path ------------------------------------------------------------------------------------------
     def encode(self, x):
         """Embedder.forward, mapping 'posenc' (models/vanilla.py:60-79,90-92): [x, sin(f0 x), cos(f0 x), sin(f1 x), ...]."""
-        pe = self.pos_pe
-        if pe.mapping != 'posenc':
+        if self.pos_pe.mapping != 'posenc':
             raise NotImplementedError("offset nets use the 'posenc' mapping (models/vanilla.py:180-188)")
-        freqs = 2.0 ** torch.linspace(pe.min_freq, pe.max_freq, steps=pe.N_freqs, device=x.device)
         out = [x]
-        for f in freqs:
+        for f in _offset_freqs(self, x.device):
             out += [torch.sin(x * f), torch.cos(x * f)]
         return torch.cat(out, -1)
 
-    def forward(self, input_pts, cur_iter=None):
-        assert cur_iter is None                                          # (:91)
+    def forward_library(self, input_pts):
         import torch.nn.functional as F
         n = self.nerf
         e = self.encode(input_pts)
@@ -138,14 +145,149 @@ class OffsetNet(nn.Module):
             h = F.relu(lin(h))
             if i in n.skips:
                 h = torch.cat([e, h], -1)
-        out = n.output_linear(h)
-        if n.scale_type == 'no':
-            return out
-        if n.scale_type == 'linear':
-            return out * n.scale
-        if n.scale_type == 'tanh':
-            return torch.tanh(out) * n.scale
-        raise ValueError(n.scale_type)
+        return _offset_scaled(self, n.output_linear(h))
+
+    # ---- tensor-core path (module-level functions below: they also serve the reference's own OffsetNet instances) ----
+    def tc_supported(self):
+        return offset_tc_supported(self)
+
+    def joiner_weights(self, t):
+        return offset_joiner_weights(self, t)
+
+    def forward_at_time(self, pts, t):
+        """pts [...,3] CUDA, t: the step's time (float or 0-d tensor) -> offsets [...,3] on the tensor-core kernels."""
+        return offset_forward_at_time(self, pts, t)
+
+    def forward(self, input_pts, cur_iter=None):
+        assert cur_iter is None                                          # (:91)
+        out = offset_forward_tc_if_constant_time(self, input_pts)
+        return self.forward_library(input_pts) if out is None else out
+
+
+def _offset_freqs(net, device=None):
+    pe = net.pos_pe
+    return 2.0 ** torch.linspace(pe.min_freq, pe.max_freq, steps=pe.N_freqs, device=device)
+
+
+def _offset_scaled(net, out):
+    n = net.nerf
+    if n.scale_type == 'no':
+        return out
+    if n.scale_type == 'linear':
+        return out * n.scale
+    if n.scale_type == 'tanh':
+        return torch.tanh(out) * n.scale
+    raise ValueError(n.scale_type)
+
+
+def offset_tc_supported(net):
+    """True for the reference's default offset-net architecture (models/vanilla.py:180-205 with options/options.py defaults)."""
+    try:
+        n, pe = net.nerf, net.pos_pe
+        return bool(pe.mapping == 'posenc' and pe.input_dims == 4 and pe.N_freqs == 10 and pe.log_sampling and pe.include_input
+                    and len(n.pts_linears) == 8 and tuple(n.pts_linears[1].weight.shape) == (256, 256)
+                    and tuple(n.skips) == (4,) and not n.use_viewdirs and tuple(n.output_linear.weight.shape) == (3, 256))
+    except AttributeError:
+        return False
+
+
+def offset_channel_split(n_freqs):
+    """Indices of the 63 spatial and the 21 time channels inside the 84-channel encoding of (x, y, z, t)
+    (models/vanilla.py:60-79: identity, then sin and cos of all four inputs per frequency)."""
+    xyz, tt = [0, 1, 2], [3]
+    for k in range(n_freqs):
+        s, c = 4 + 8 * k, 4 + 8 * k + 4
+        xyz += [s, s + 1, s + 2, c, c + 1, c + 2]
+        tt += [s + 3, c + 3]
+    return xyz, tt
+
+
+def offset_joiner_weights(net, t):
+    """The Joiner-shaped parameters equivalent to offset network `net` at time t (0-d tensor or float), as differentiable
+    functions of its parameters; keys = NeRF(use_viewdirs=True).named_parameters() names."""
+    n = net.nerf
+    dev = n.output_linear.weight.device
+    xyz, tt = offset_channel_split(net.pos_pe.N_freqs)
+    xyz_i, tt_i = torch.tensor(xyz, device=dev), torch.tensor(tt, device=dev)
+    t = torch.as_tensor(t, dtype=torch.float32, device=dev).reshape(())
+    pe_t = [t[None]]
+    for f in _offset_freqs(net, dev):
+        pe_t += [torch.sin(t * f)[None], torch.cos(t * f)[None]]
+    pe_t = torch.cat(pe_t)                                           # [21]
+    n_in = net.pos_pe.out_dim                                        # 84
+    W = {}
+    for l, lin in enumerate(n.pts_linears):
+        w, b = lin.weight, lin.bias
+        if l == 0:
+            W['pts_linears.0.weight'] = w[:, xyz_i]
+            W['pts_linears.0.bias'] = b + w[:, tt_i] @ pe_t
+        elif (l - 1) in n.skips:
+            W[f'pts_linears.{l}.weight'] = torch.cat([w[:, xyz_i], w[:, n_in:]], 1)
+            W[f'pts_linears.{l}.bias'] = b + w[:, tt_i] @ pe_t
+        else:
+            W[f'pts_linears.{l}.weight'], W[f'pts_linears.{l}.bias'] = w, b
+    wo, bo = n.output_linear.weight, n.output_linear.bias
+    z = lambda *s: torch.zeros(*s, device=dev)
+    W['feature_linear.weight'] = torch.cat([wo, -wo, z(250, 256)], 0)
+    W['feature_linear.bias'] = torch.cat([bo, -bo, z(250)])
+    W['alpha_linear.weight'], W['alpha_linear.bias'] = z(1, 256), z(1)
+    vw = z(128, 256 + 27)
+    vw[torch.arange(6), torch.arange(6)] = 1.0
+    W['views_linears.0.weight'], W['views_linears.0.bias'] = vw, z(128)
+    rw = z(3, 128)
+    rw[torch.arange(3), torch.arange(3)] = 1.0
+    rw[torch.arange(3), torch.arange(3) + 3] = -1.0
+    W['rgb_linear.weight'], W['rgb_linear.bias'] = rw, z(3)
+    return W
+
+
+def offset_shadow_joiner(net):
+    """The Joiner module whose parameters receive offset_joiner_weights() before every launch (the kernels pack from
+    it).  Kept in the instance dict inside a tuple so that it never shows up among the offset net's own parameters."""
+    dev = net.nerf.output_linear.weight.device
+    sh = net.__dict__.get('_nm_shadow')
+    if sh is None or next(sh[0].parameters()).device != dev:
+        pe = net.pos_pe
+        pos = Embedder(3, pe.max_freq, pe.N_freqs, pe.log_sampling, pe.include_input, min_freq=pe.min_freq)
+        dpe = Embedder(3, 3, 4, True, True)
+        j = Joiner(pos, dpe, NeRF(depth=8, width=256, input_ch=pos.out_dim, input_ch_views=dpe.out_dim, use_viewdirs=True)).to(dev)
+        for p in j.parameters():
+            p.requires_grad_(False)
+        sh = (j,)
+        net.__dict__['_nm_shadow'] = sh
+    return sh[0]
+
+
+def offset_forward_at_time(net, pts, t):
+    from . import autograd
+    j = offset_shadow_joiner(net)
+    W = offset_joiner_weights(net, t)
+    names = [k for k, _ in j.nerf.named_parameters()]
+    with torch.no_grad():
+        for k, p in j.nerf.named_parameters():
+            p.copy_(W[k])
+    shape = pts.shape[:-1]
+    x = pts.detach().float().reshape(-1, 3).contiguous()
+    views = torch.zeros_like(x)
+    if torch.is_grad_enabled() and any(p.requires_grad for p in net.nerf.parameters()):
+        raw = autograd._JoinerMLP.apply(x, views, j, *[W[k] for k in names])
+    else:
+        raw = ops.joiner_forward(j, x, views)
+    return _offset_scaled(net, raw[:, :3]).reshape(*shape, 3)
+
+
+def offset_forward_tc_if_constant_time(net, input_pts):
+    """OffsetNet.forward on the tensor-core path when it applies: CUDA input [...,4] whose time column is one value (what
+    trainers/human_nerf_trainer.py:260 builds) and the default architecture.  Returns None otherwise.  The constancy check
+    is one host read per call; callers that know the step's time use forward_at_time / offset_forward_at_time directly."""
+    if not (isinstance(input_pts, torch.Tensor) and input_pts.is_cuda and input_pts.shape[-1] == 4 and input_pts.numel()
+            and offset_tc_supported(net) and net.nerf.output_linear.weight.is_cuda):
+        return None
+    tcol = input_pts[..., 3]
+    t0 = tcol.reshape(-1)[0]
+    if not bool((tcol == t0).all()):
+        return None
+    return offset_forward_at_time(net, input_pts[..., :3], t0.detach())
 
 
 def build_offset_net(opt):

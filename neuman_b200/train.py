@@ -114,7 +114,8 @@ def eval_human_samples(net, batch, opt, faces, offset_net=None, t_rand=None, act
     (the reference reads them from the capture's posed mesh, :268); offset_net: one of net.offset_nets (the reference draws
     `random.choice(self.net.offset_nets)`, :261) or None to skip the offset.
 
-    Stages: ray_to_samples kernel (:248-257) -> offset network (:260-261; library GEMMs for now) -> vertex_forward
+    Stages: ray_to_samples kernel (:248-257) -> offset network (:260-261; the step's time is one number, so the network
+    runs as a Joiner on the tensor-core kernels, models.OffsetNet) -> vertex_forward
     training kernels (:264) -> closest-face query on the device BVH + fused blend / inverse / apply / offset / directions
     (:265-276, nm_signed_distance + nm_human_canonicalize) -> canonical human network on the tensor-core training kernel
     (:277).  loss.backward() then runs the adjoint kernels of every stage: gradients reach the human network, the offset
@@ -128,8 +129,12 @@ def eval_human_samples(net, batch, opt, faces, offset_net=None, t_rand=None, act
     human_b, human_n, _ = human_pts.shape
     offset = None
     if offset_net is not None:
-        cur_time = torch.ones_like(human_pts[..., 0:1]) * float(batch['cur_view_f'])
-        offset = offset_net(torch.cat([human_pts, cur_time], dim=-1))
+        from . import models
+        if human_pts.is_cuda and models.offset_tc_supported(offset_net):
+            offset = models.offset_forward_at_time(offset_net, human_pts, float(batch['cur_view_f']))   # tensor-core kernels
+        else:
+            cur_time = torch.ones_like(human_pts[..., 0:1]) * float(batch['cur_view_f'])
+            offset = offset_net(torch.cat([human_pts, cur_time], dim=-1))
     mesh, raw_Ts = net.vertex_forward(int(batch['cap_id']))
     can_pts, can_dirs, _, _ = ops.eval_human_samples(human_pts, mesh[0], faces, raw_Ts[0], offset=offset, actor=actor)
     human_out = net.coarse_human_net(can_pts, can_dirs)

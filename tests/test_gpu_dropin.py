@@ -189,6 +189,13 @@ def _reference_human_trainer_case(ref, device):
     faces = net.body_model.faces_tensor.cpu()
     cap = types.SimpleNamespace(posed_mesh_cpu=types.SimpleNamespace(faces_packed=lambda: faces))
     me = types.SimpleNamespace(opt=opt, net=net, val_dataset=types.SimpleNamespace(scene=types.SimpleNamespace(captures=[cap])))
+    if device == "cpu":
+        # the reference's 'rotate' Embedder puts its frequency matrix on the GPU whenever one is visible, whatever device
+        # the module is meant for (models/vanilla.py:53-56): bring it back for the CPU run of the unpatched reference
+        for j in (net.coarse_human_net, net.coarse_bkg_net, net.fine_bkg_net):
+            for pe in (j.pos_pe, j.dir_pe):
+                if hasattr(pe, "bvals"):
+                    pe.bvals = pe.bvals.cpu()
     return me, net
 
 

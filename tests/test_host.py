@@ -252,3 +252,37 @@ def test_batchers_host_logic_equals_the_reference_datasets(monkeypatch):
                         lambda cap, verts, thr: torch.from_numpy(g["hu_cap%d_cache" % (0 if cap.image.shape[0] == 48 else 1)]))
     T.test_background_batches_equal_the_reference_dataset()
     T.test_human_batches_equal_the_reference_dataset()
+
+
+@pytest.mark.parametrize("t", [0.0, 3 / 11, 0.97])
+def test_offset_net_as_joiner_weights_are_equivalent(t):
+    """models.offset_joiner_weights: for a fixed time the offset network IS a Joiner on (x, y, z) -- time channels folded
+    into the layer-0 / skip-layer biases, output_linear carried through the non-negative head as relu(y) - relu(-y).  The
+    oracle's Joiner on the synthesized weights must reproduce the library forward, gradients to the offset net's own
+    parameters included (autograd through the synthesis)."""
+    from neuman_b200 import models
+    from oracle import neuman_oracle as no
+    opt = nb.default_opt(use_cuda=False, num_offset_nets=1, offset_scale=0.7, offset_scale_type='tanh', pos_min_freq=0)
+    torch.manual_seed(5)
+    net = nb.build_offset_net(opt)
+    assert net.tc_supported()
+    x = torch.randn(300, 3)
+    lib = net(torch.cat([x, torch.full((300, 1), t)], -1))
+    W = net.joiner_weights(t)
+    j = models.offset_shadow_joiner(net)
+    assert sorted(W) == sorted(k for k, _ in j.nerf.named_parameters())
+    assert all(tuple(W[k].shape) == tuple(p.shape) for k, p in j.nerf.named_parameters())
+    assert len(net.state_dict()) == 18 and not any("shadow" in k for k in net.state_dict())      # checkpoints unchanged
+    P = no.NetParams(sd={'nerf.' + k: v for k, v in W.items()},
+                     pos_pe=no.PESpec(kind='posenc', min_freq=0.0, max_freq=9.0, n_freqs=10, include_input=True))
+    raw = no.net_forward(P, x, torch.zeros_like(x))
+    out = models._offset_scaled(net, raw[:, :3])
+    assert (out - lib).abs().max() < 1e-6
+    w = torch.randn(300, 3)
+    params = list(net.nerf.parameters())
+    g1 = torch.autograd.grad((lib * w).sum(), params, retain_graph=True)
+    g2 = torch.autograd.grad((out * w).sum(), params)
+    for a, b in zip(g1, g2):
+        assert (a - b).abs().max() < 1e-5 * (1 + a.abs().max())
+    xyz, tt = models.offset_channel_split(10)
+    assert sorted(xyz + tt) == list(range(84)) and len(xyz) == 63

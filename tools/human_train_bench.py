@@ -118,8 +118,14 @@ def main():
     def off_fb():
         for p in on.parameters():
             p.grad = None
-        on(torch.cat([pts, torch.ones_like(pts[..., :1]) * 0.3], -1)).sum().backward()
+        on.forward_library(torch.cat([pts, torch.ones_like(pts[..., :1]) * 0.3], -1)).sum().backward()
     out["offset_net_library_fwd_bwd_ms"] = timed(off_fb, warm=2, reps=5)
+
+    def off_tc():
+        for p in on.parameters():
+            p.grad = None
+        on.forward_at_time(pts, 0.3).sum().backward()
+    out["offset_net_tensor_core_fwd_bwd_ms"] = timed(off_tc)
     cp, cd = nag.human_canonicalize(pts, verts, T, f_id, closest, F, None)
 
     def net_fb():
