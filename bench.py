@@ -311,6 +311,12 @@ def main():
     if not args.no_configs:
         side = side_configs(nb, render, sharding, scenes, ctx, dev, rank, world, dist, pk)
     train = train_step_ms(nb, dev) if (world == 1 and not args.no_configs) else None
+    human_train = None
+    if world == 1 and not args.no_configs:
+        try:
+            human_train = human_train_step_ms(nb, dev)
+        except Exception as e:                         # a side measurement must never cost the line
+            human_train = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
         mlp_ms_per_launch = prof["mlp_ms"] / max(prof["mlp_launches"], 1)
@@ -338,6 +344,7 @@ def main():
                     "api": "neuman_b200.render_vanilla(coarse, cap, fine_net=fine, ...) -> numpy rgb [720,1280,3] + depth (reference signature); "
                            "inputs = the capture's K / camera_to_world (208 B host struct), rays are generated on the device"},
             "gpu_launches": int(launches), "clocks": clocks, "configs": side, "train_step": train,
+            "human_train_step": human_train,
         }
         if not args.no_cpu_baseline and world == 1:
             arm = CpuArm()
@@ -379,6 +386,58 @@ def train_step_ms(nb, dev, R=2048, steps=20):
     ms = e0.elapsed_time(e1) / steps
     return {"ms_per_step": ms, "rays_per_s": R / ms * 1e3, "rays_per_batch": R, "samples": "128+128", "mlp_evals_per_step": R * 384,
             "loss_finite": bool(torch.isfinite(loss)), "what": "neuman_b200.train.train_batch: CUDA forward/backward kernels + torch.optim.Adam"}
+
+
+def human_train_step_ms(nb, dev, R=2048, S=128, steps=10):
+    """the human branch of one HumanNeRFTrainer step (trainers/human_nerf_trainer.py:241-278,
+    `_eval_human_samples`, then backward + Adam) on the CUDA path at the reference's defaults (2048 rays x 128 samples):
+    ray_to_samples, offset network (tensor-core kernels), SMPL vertex_forward (training kernels), closest-face query,
+    fused blend / inverse / apply / directions, canonical human network -- and the adjoint of each, down to the human and
+    offset networks' weights and the per-frame poses / betas / alignments."""
+    from neuman_b200 import train as nt
+    from neuman_b200.synthetic import make_model
+    rng = np.random.RandomState(0)
+    pose, betas = rng.normal(0, 0.3, (1, 72)).astype(np.float32), rng.normal(0, 1.0, (1, 10)).astype(np.float32)
+    align = np.eye(4, dtype=np.float32)
+    align[3, :3] = (0.3, -0.1, 2.0)
+    opt = nb.default_opt(use_cuda=True, num_offset_nets=1, offset_scale=0.02, offset_scale_type='tanh', samples_per_ray=S)
+    torch.manual_seed(0)
+    model = make_model(0)
+    net = nb.HumanNeRF(opt, poses=pose, betas=betas, alignments=align[None], scale=0.4, smpl_model=model)
+    faces = np.ascontiguousarray(model["f"][:, :3].astype(np.int64))
+    with torch.no_grad():
+        V0 = net.vertex_forward(0)[0][0]
+    g = torch.Generator(device=dev).manual_seed(0)
+    eye = V0.mean(0) + torch.tensor([0.0, 0.0, -2.0], device=dev)
+    d = V0[torch.randint(0, V0.shape[0], (R,), device=dev, generator=g)] + 0.02 * torch.randn(R, 3, device=dev, generator=g) - eye
+    dist = d.norm(dim=1, keepdim=True)
+    batch = {'origin': eye[None].repeat(R, 1), 'direction': d / dist, 'human_near': dist - 0.2, 'human_far': dist + 0.2,
+             'cur_view_f': 3 / 11, 'cap_id': 0}
+    params = (list(net.coarse_human_net.parameters()) + list(net.offset_nets.parameters())
+              + [net.poses, net.betas, net.alignments])
+    optim = torch.optim.Adam(params, lr=1e-4)
+
+    def step():
+        optim.zero_grad()
+        out = nt.eval_human_samples(net, batch, opt, faces, offset_net=net.offset_nets[0])
+        loss = out[5].square().mean()
+        loss.backward()
+        optim.step()
+        return loss
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ok = bool(torch.isfinite(loss)) and all(bool(torch.isfinite(p).all()) for p in (net.poses, net.betas, net.alignments))
+    return {"ms_per_step": ms, "rays_per_s": R / ms * 1e3, "rays_per_batch": R, "samples": S, "mlp_evals_per_step": 2 * R * S,
+            "finite": ok, "what": "neuman_b200.train.eval_human_samples (offset net + SMPL + warp + human net on the CUDA kernels) "
+                                  "+ backward + torch.optim.Adam over the nets and poses / betas / alignments"}
 
 
 def side_configs(nb, render, sharding, scenes, ctx, dev, rank, world, dist, pk):
