@@ -191,8 +191,10 @@ def test_eval_human_samples_end_to_end():
     _close(net.poses.grad.cpu()[0], po.grad[0], 1e-3, "dposes")
     _close(net.betas.grad.cpu()[0], bo.grad[0], 1e-3, "dbetas")
     _close(net.alignments.grad.cpu()[0], ao.grad, 1e-3, "dalignments")
+    # the offset network runs on the tensor-core kernels (fp16 operands): the Joiner's gradient tolerance (tests/test_gpu_train.py)
     for (k, pm), po_ in zip(net.offset_nets[0].named_parameters(), off_cpu.parameters()):
-        _close(pm.grad.cpu(), po_.grad, 1e-3, "offset net " + k)
+        g, g_o = pm.grad.cpu().numpy(), po_.grad.numpy()
+        assert np.isfinite(g).all() and np.abs(g - g_o).max() < 8e-2 * np.abs(g_o).max() + 1e-7, ("offset net " + k, np.abs(g - g_o).max(), np.abs(g_o).max())
     net.zero_grad()
     po.grad = bo.grad = ao.grad = None
     w3 = rng.normal(0, 1, (R, S, 4)).astype(np.float32)
