@@ -9,7 +9,9 @@ with torch ops on whatever device the frames live on (float64 inside, like sciki
 
 scikit-image, imageio and lpips are not in this image: the formulas are restated from the published definitions
 (oracle/metrics_oracle.py restates them once more with scipy's uniform_filter, the routine scikit-image itself
-calls); parity with the libraries themselves is unpinned.  LPIPS needs the AlexNet weights and is not built.
+calls); parity with the libraries themselves is unpinned.  What IS pinned against third-party code present here
+(tests/test_host.py::test_frame_metrics_against_opencv): PSNR against OpenCV's cv2.PSNR, the PNG file against OpenCV's
+decoder, the SSIM window statistics against cv2.blur's box filter.  LPIPS needs the AlexNet weights and is not built.
 """
 import numpy as np
 import torch

@@ -228,6 +228,31 @@ def test_frame_metrics_match_the_oracle(tmp_path):
     assert set(r) == {"ssim", "psnr"} and np.isinf(r["psnr"])
 
 
+def test_frame_metrics_against_opencv(tmp_path):
+    """Third-party pins available in this image (scikit-image / imageio are not): OpenCV's own PSNR for uint8 frames
+    (cv2.PSNR, R = 255) and its PNG decoder on the file save_png wrote; SSIM's window means against cv2.blur's box filter
+    (an independent implementation of the uniform window the scikit-image formula averages over)."""
+    cv2 = pytest.importorskip("cv2")
+    from neuman_b200 import metrics
+    rng = np.random.RandomState(1)
+    gt = rng.randint(0, 256, (41, 57, 3)).astype(np.uint8)
+    pred = np.clip(gt.astype(np.float64) + rng.normal(0, 9, gt.shape), 0, 255).astype(np.uint8)
+    assert abs(metrics.psnr(gt, pred) - cv2.PSNR(gt, pred)) < 1e-9
+    f = rng.uniform(0, 1, (9, 11, 3)).astype(np.float32)
+    metrics.save_png(str(tmp_path / "b.png"), f)
+    bgr = cv2.imread(str(tmp_path / "b.png"), cv2.IMREAD_COLOR)
+    assert np.array_equal(bgr[..., ::-1], metrics.to_uint8(f).numpy())
+    # SSIM of one channel from cv2's box filter (BORDER_REFLECT_101 borders are cropped away exactly as scikit-image crops)
+    x, y = pred[..., 0].astype(np.float64), gt[..., 0].astype(np.float64)
+    box = lambda a: cv2.blur(a, (7, 7))[3:-3, 3:-3]
+    ux, uy = box(x), box(y)
+    cn = 49 / 48.0
+    vx, vy, vxy = cn * (box(x * x) - ux * ux), cn * (box(y * y) - uy * uy), cn * (box(x * y) - ux * uy)
+    C1, C2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+    assert abs(metrics.ssim(pred[..., :1], gt[..., :1]) - S.mean()) < 1e-9
+
+
 def test_batchers_host_logic_equals_the_reference_datasets(monkeypatch):
     """The host logic of neuman_b200.data (segment plan, patch window, gathers, near/far cache lookup, dtypes) on CPU
     tensors against the batches the UNMODIFIED reference datasets produced (tests/golden/batches.npz): the ray kernel
