@@ -202,11 +202,20 @@ def _reference_human_trainer_case(ref, device):
 def test_reference_human_trainer_step_runs_on_the_cuda_path(ref):
     """install(train=True) under the reference's own HumanNeRFTrainer._eval_human_samples
     (trainers/human_nerf_trainer.py:241-278) and loss.backward(): ray_to_samples, vertex_forward (SMPL training kernels),
-    warp_samples_to_canonical_diff (device BVH query + blend/inverse kernel), Joiner.forward (tensor-core training kernel) and
-    their adjoints, against the SAME method of the unpatched reference on the CPU."""
+    warp_samples_to_canonical_diff (device BVH query + blend/inverse kernel), OffsetNet.forward and Joiner.forward (tensor-core
+    training kernels) and their adjoints, against the SAME method of the unpatched reference on the CPU.
+
+    The closest face / point of every sample is a CONSTANT of the step in the reference (libigl's numpy answer, :265-270), and
+    where the closest point lies on an edge both adjacent faces are exact answers: the blended transform is the same for
+    either, but its derivative with respect to the vertices is not (the barycentric formula projects onto the chosen face's
+    plane).  Which one libigl reports is its tie rule (unpinned), so the CPU run is given the device query's
+    answers: values and gradients are then compared on identical constants."""
     import importlib
+    import sys
     tr = importlib.import_module("trainers.human_nerf_trainer")
-    from neuman_b200 import dropin
+    from neuman_b200 import dropin, ops
+    igl_stub = sys.modules["igl"]
+    stub_sd, ops_sd = igl_stub.signed_distance, ops.signed_distance
     dropin.uninstall()
     try:
         me_c, net_c = _reference_human_trainer_case(ref, "cpu")
@@ -222,35 +231,50 @@ def test_reference_human_trainer_step_runs_on_the_cuda_path(ref):
                           "human_near": torch.from_numpy(dist - 0.15).float().to(dev),
                           "human_far": torch.from_numpy(dist + 0.15).float().to(dev), "cur_view_f": torch.tensor(3 / 11), "cap_id": 0}
         w = torch.from_numpy(rng.normal(0, 1, (R, 24, 3)).astype(np.float32))
-        out_c = quiet(tr.HumanNeRFTrainer._eval_human_samples, me_c, mk("cpu"), "cpu")
-        ((out_c[3] * w).sum() + (out_c[4] * w.flip(0)).sum()).backward()
-        # ---- the same call with the CUDA path installed ----
+        # ---- the reference's method with the CUDA path installed; the device query's answers are recorded ----
         nb.install(ref_import.REF_ROOT, train=True)
         me_g, net_g = _reference_human_trainer_case(ref, "cuda")
         net_g.load_state_dict(net_c.state_dict())
+        seen = []
+
+        def recording_sd(*a, **k):
+            out = ops_sd(*a, **k)
+            seen.append(tuple(np.asarray(o.cpu() if isinstance(o, torch.Tensor) else o) for o in out))
+            return out
+        ops.signed_distance = recording_sd
         l0 = launches()
         out_g = quiet(tr.HumanNeRFTrainer._eval_human_samples, me_g, mk("cuda"), "cuda")
         ((out_g[3] * w.cuda()).sum() + (out_g[4] * w.flip(0).cuda()).sum()).backward()
+        ops.signed_distance = ops_sd
         assert launches() - l0 >= 12, "the reference's trainer step did not reach libneuman_b200"
-        assert all(o.is_cuda for o in out_g)
+        assert all(o.is_cuda for o in out_g) and len(seen) == 1
+        # ---- the same method of the unpatched reference on the CPU, on the same closest faces / points ----
+        dropin.uninstall()
+        S_d, I_d, C_d = seen[0]
+        igl_stub.signed_distance = lambda P, V, F, *a, **k: (S_d.astype(np.float64), I_d.astype(np.int32), C_d.astype(np.float64))
+        out_c = quiet(tr.HumanNeRFTrainer._eval_human_samples, me_c, mk("cpu"), "cpu")
+        igl_stub.signed_distance = stub_sd
+        ((out_c[3] * w).sum() + (out_c[4] * w.flip(0)).sum()).backward()
         assert np.abs(out_g[0].detach().cpu().numpy() - out_c[0].detach().numpy()).max() < 2e-6          # human_pts
-        e = np.abs(out_g[3].detach().cpu().numpy() - out_c[3].detach().numpy()).max(-1)                   # can_pts
-        # two independent queries (float64 exhaustive on the CPU vertices, fp32 BVH arg-min on the device's): the closest
-        # point moves by an ulp, and on thin triangles the cross-product barycentrics amplify that (measured: 0.7 % of the
-        # samples above 5e-6, max 8e-5); a medial-axis tie would show as a jump of millimetres
-        assert np.median(e) < 2e-6 and (e > 2e-4).mean() < 0.005, (np.median(e), (e > 2e-4).mean(), e.max())
-        ok = e <= 1e-5
-        assert np.abs(out_g[5].detach().cpu().numpy() - out_c[5].detach().numpy())[ok].max() < 2e-3      # human_out (11-bit operands)
+        assert np.abs(out_g[3].detach().cpu().numpy() - out_c[3].detach().numpy()).max() < 1e-5          # can_pts (+ offset)
+        assert np.abs(out_g[4].detach().cpu().numpy() - out_c[4].detach().numpy()).max() < 2e-4          # can_dirs (1 / spacing)
+        assert np.abs(out_g[5].detach().cpu().numpy() - out_c[5].detach().numpy()).max() < 2e-3          # human_out (11-bit operands)
         for name in ("poses", "betas", "alignments"):
             g, c = getattr(net_g, name).grad.cpu().numpy(), getattr(net_c, name).grad.numpy()
-            assert np.isfinite(g).all() and np.abs(g - c).max() < 2e-2 * (1 + np.abs(c).max()), (name, np.abs(g - c).max(), np.abs(c).max())
+            assert np.isfinite(g).all() and np.abs(g - c).max() < 5e-3 * (1 + np.abs(c).max()), (name, np.abs(g - c).max(), np.abs(c).max())
         g, c = net_g.offset_nets[0].nerf.output_linear.weight.grad.cpu().numpy(), net_c.offset_nets[0].nerf.output_linear.weight.grad.numpy()
-        assert np.abs(g - c).max() < 2e-2 * (1 + np.abs(c).max())
-        # the human network's own gradients come from a second loss through its output
+        assert np.abs(g - c).max() < 8e-2 * np.abs(c).max() + 1e-7, (np.abs(g - c).max(), np.abs(c).max())   # tensor-core operands
+        # the device's own query against the reference stub's (float64, exhaustive) on the same points: same distances
+        S_r, I_r, C_r = stub_sd(out_c[0].detach().numpy().astype(np.float64), V0.astype(np.float64), me_c.val_dataset.scene.captures[0].posed_mesh_cpu.faces_packed().numpy())
+        assert np.abs(np.abs(S_d) - np.abs(S_r)).max() < 1e-5
+        # the human network's own gradients come from a loss through its output
+        nb.install(ref_import.REF_ROOT, train=True)
         net_g.zero_grad()
         out_g = quiet(tr.HumanNeRFTrainer._eval_human_samples, me_g, mk("cuda"), "cuda")
         out_g[5].square().mean().backward()
         assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net_g.coarse_human_net.parameters())
         assert net_g.poses.grad is not None and torch.isfinite(net_g.poses.grad).all()
     finally:
+        ops.signed_distance = ops_sd
+        igl_stub.signed_distance = stub_sd
         nb.install(ref_import.REF_ROOT)             # back to the module fixture's state (inference drop-in)
