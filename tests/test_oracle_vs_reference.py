@@ -229,3 +229,87 @@ def test_mirror_human_nerf_state_dict_matches_the_reference(ref):
         assert sr[k].shape == sm[k].shape and torch.equal(sr[k], sm[k]), k
     assert any(k.startswith("offset_nets.1.nerf.output_linear") for k in sm)
     m.load_state_dict(sr, strict=True)
+
+
+def _reference_human_net(ref):
+    """The reference's HumanNeRF with per-frame SMPL parameters on the CPU, assembled as models/human_nerf.py:31-90 does
+    (the hard-coded SMPL pickle path is licence-gated and absent: a synthetic SMPL-shaped pickle instead)."""
+    torch.manual_seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = ref.human_nerf.HumanNeRF(ref_opts.default_opt(num_offset_nets=1))
+    rng = np.random.RandomState(6)
+    pose, betas = rng.normal(0, 0.3, (1, 72)).astype(np.float32), rng.normal(0, 1, (1, 10)).astype(np.float32)
+    align = np.eye(4, dtype=np.float32)
+    align[:3, :3] = np.array([[np.cos(0.2), 0, np.sin(0.2)], [0, 1, 0], [-np.sin(0.2), 0, np.cos(0.2)]])
+    align = align.T.copy()
+    align[3, :3] = (0.3, -0.1, 2.0)
+    P = torch.nn.Parameter
+    net.poses, net.betas, net.alignments, net.scale = P(torch.from_numpy(pose)), P(torch.from_numpy(betas)), P(torch.from_numpy(align[None])), 0.4
+    pk = os.path.join(tempfile.mkdtemp(), "SMPL_NEUTRAL.pkl")
+    synth_smpl.write_pickle(pk, 0)
+    net.body_model = ref.smpl.SMPL(pk, gender="neutral", device=torch.device("cpu"))
+    da = torch.zeros(24, 3)
+    da[1, 2], da[2, 2] = 1.0, -1.0
+    net.da_smpl = P(da.reshape(1, -1), requires_grad=False)
+    return net
+
+
+def test_vertex_forward_and_its_gradients_match(ref):
+    """oracle.vertex_forward (what the SMPL training kernels and their adjoint are checked against) vs the reference's
+    HumanNeRF.vertex_forward (models/human_nerf.py:92-122): values and the gradients loss.backward() sends to
+    poses / betas / alignments."""
+    net = _reference_human_net(ref)
+    w_r, T_r = net.vertex_forward(0)
+    model = synth_smpl.torch_model(0)
+    po, bo = net.poses.detach().clone().requires_grad_(True), net.betas.detach().clone().requires_grad_(True)
+    ao = net.alignments.detach()[0].clone().requires_grad_(True)
+    w_o, T_o = no.vertex_forward(model, po, bo, ao, 0.4)
+    assert (w_r - w_o).abs().max() < 1e-6 and (T_r - T_o).abs().max() < 1e-6
+    rng = np.random.RandomState(0)
+    g1 = torch.from_numpy(rng.normal(0, 1, tuple(T_r.shape)).astype(np.float32))
+    g2 = torch.from_numpy(rng.normal(0, 1, tuple(w_r.shape)).astype(np.float32))
+    ((T_r * g1).sum() + (w_r * g2).sum()).backward()
+    ((T_o * g1).sum() + (w_o * g2).sum()).backward()
+    for a, b in ((net.poses.grad, po.grad), (net.betas.grad, bo.grad), (net.alignments.grad[0], ao.grad)):
+        assert (a - b).abs().max() < 1e-5 * (1 + b.abs().max())
+
+
+def test_differentiable_warp_matches_and_its_vertex_gradient_depends_on_the_tie_rule(ref):
+    """oracle.warp_diff_Tinv vs the reference's warp_samples_to_canonical_diff (utils/ray_utils.py:69-93) on the same query
+    answers.  Then the property that makes libigl's tie rule matter for TRAINING: where the closest point
+    lies on an edge, both adjacent faces give the same inverse transform, but a different gradient with respect to the
+    vertices."""
+    from oracle import mesh_oracle as mo
+    body = synth_smpl.random_body(seed=3)
+    V = torch.from_numpy(body["verts"]).float().requires_grad_(True)
+    F = np.asarray(body["faces"])[:, :3]
+    T = torch.from_numpy(body["Ts"][:6890]).float().requires_grad_(True)
+    rng = np.random.RandomState(0)
+    P = (body["verts"][rng.randint(0, 6890, 400)] + rng.normal(0, 0.03, (400, 3))).astype(np.float32)
+    Ti_ref, f_id, sd = ref.ray_utils.warp_samples_to_canonical_diff(P, V, F, T)
+    S, I, C = mo.signed_distance(P, body["verts"], F)
+    assert np.array_equal(f_id, I)
+    Ti = no.warp_diff_Tinv(C, I, V, F, T)
+    assert (Ti - Ti_ref).abs().max() == 0
+    # the other face of every edge-region sample
+    L = mo.barycentric_coordinates_tri(C, *(body["verts"][F[I, k]].astype(np.float64) for k in range(3)))
+    edges = {}
+    for f, tri in enumerate(F):
+        for e in ((tri[0], tri[1]), (tri[1], tri[2]), (tri[2], tri[0])):
+            edges.setdefault((min(e), max(e)), []).append(f)
+    I2, flipped = I.copy(), 0
+    for r in range(len(I)):
+        z = np.flatnonzero(np.abs(L[r]) < 1e-9)
+        if len(z) == 1:
+            tri = F[I[r]]
+            e = (tri[(z[0] + 1) % 3], tri[(z[0] + 2) % 3])
+            other = [f for f in edges[(min(e), max(e))] if f != I[r]]
+            if other:
+                I2[r], flipped = other[0], flipped + 1
+    assert flipped > 40                                                    # edge regions are common, not a corner case
+    Ti2 = no.warp_diff_Tinv(C, I2, V, F, T)
+    assert (Ti2 - Ti).abs().max() < 1e-5 * Ti.abs().max()                 # same transform ...
+    w = torch.from_numpy(rng.normal(0, 1, tuple(Ti.shape)).astype(np.float32))
+    gV1 = torch.autograd.grad((Ti * w).sum(), V, retain_graph=True)[0]
+    gV2 = torch.autograd.grad((Ti2 * w).sum(), V)[0]
+    assert (gV1 - gV2).abs().max() > 0.05 * gV1.abs().max()               # ... different gradient to the vertices
