@@ -280,8 +280,7 @@ def joiner_forward(joiner, input_pts, input_views):
 # Human trainer: differentiable observation -> canonical map and SMPL scene transforms (csrc/human_train.cu, smpl.cu)
 # ---------------------------------------------------------------------------------------------
 def _faces_i32(faces, device):
-    f = faces if isinstance(faces, torch.Tensor) else torch.as_tensor(__import__("numpy").asarray(faces))
-    return f[:, :3].to(device=device, dtype=torch.int32).contiguous()
+    return ops.faces_device(faces, device)
 
 
 class _WarpDiffTinv(torch.autograd.Function):

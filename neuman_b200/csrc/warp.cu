@@ -43,10 +43,34 @@ __device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
 }
 
 // packed triangles + Morton keys of the centroids (key = morton30 << 32 | face: unique)
+// order-preserving float <-> int (for atomicMin / atomicMax on coordinates)
+__device__ __forceinline__ int f2ord(float f) { const int k = __float_as_int(f); return k >= 0 ? k : k ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+// bounding box of the vertices on the device (box[0..2] = min, box[3..5] = max as ordered ints; the host presets them with
+// byte patterns 0x7f / 0x80): used when the mesh comes from device memory for distance queries only, so that setting it
+// needs no device->host copy and no stream synchronisation (once per training step)
+__global__ void k_bbox(const float* __restrict__ verts, int nv, int* __restrict__ box) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int vv = v < nv ? v : nv - 1;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int k = f2ord(verts[3 * vv + c]);
+    const int lo = __reduce_min_sync(0xffffffffu, k), hi = __reduce_max_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0) { atomicMin(box + c, lo); atomicMax(box + 3 + c, hi); }
+  }
+}
+
 __global__ void k_bvh_keys(const float* __restrict__ verts, const int32_t* __restrict__ faces, int nf, float3 bmin,
-                           float3 binv, float* __restrict__ tri9, unsigned long long* __restrict__ keys) {
+                           float3 binv, const int* __restrict__ box, float* __restrict__ tri9,
+                           unsigned long long* __restrict__ keys) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= nf) return;
+  if (box) {                                   // bounds from k_bbox instead of the host's
+    bmin = make_float3(ord2f(box[0]), ord2f(box[1]), ord2f(box[2]));
+    binv = make_float3(1.f / fmaxf(ord2f(box[3]) - bmin.x, 1e-20f), 1.f / fmaxf(ord2f(box[4]) - bmin.y, 1e-20f),
+                       1.f / fmaxf(ord2f(box[5]) - bmin.z, 1e-20f));
+  }
   float v[9];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -335,7 +359,7 @@ static int ensure(nm_ctx* ctx, T** p, size_t* cap, size_t need) {
 
 // one device allocation per mesh holds the whole BVH (+ sort buffers); `cell_start` is its base pointer
 struct BvhLayout {
-  size_t keys_in, keys_out, lo, hi, children, parent, visit, leaf_face, tri9, cub_tmp, total;
+  size_t keys_in, keys_out, lo, hi, children, parent, visit, leaf_face, tri9, cub_tmp, box, total;
 };
 static BvhLayout bvh_layout(int n, size_t cub_bytes) {
   BvhLayout L;
@@ -351,6 +375,7 @@ static BvhLayout bvh_layout(int n, size_t cub_bytes) {
   L.leaf_face = take(sizeof(int32_t) * (size_t)n);
   L.tri9 = take(sizeof(float) * 9 * (size_t)n);
   L.cub_tmp = take(cub_bytes);
+  L.box = take(64);                            // device-side bounding box of the vertices (6 order-preserving ints)
   L.total = off;
   return L;
 }
@@ -389,20 +414,29 @@ extern "C" int nm_mesh_set(nm_ctx* ctx, int actor, const float* verts, int32_t n
   m.n_verts = n_verts; m.n_faces = n_faces; m.n_T = n_T;
   m.has_T = T != nullptr;
   m.pn_valid = false;
-  // bounding box on the host (82 KB; once per frame) -- only used to normalise the Morton codes
-  std::vector<float> hv((size_t)n_verts * 3);
-  if (on_device) {
-    NM_CHECK_CUDA(ctx, cudaMemcpyAsync(hv.data(), verts, hv.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
-    NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+  // Bounds of the vertices, only used to normalise the Morton codes.  Renderer meshes (with T): on the host (82 KB, once per
+  // frame), together with the vertex groups of the near/far cull.  Distance-only meshes from device memory (the trainer's
+  // per-step queries): on the device -- no copy back, no synchronisation, no cull structure (nm_impl_near_far_mesh falls
+  // back to the exhaustive loop when n_vgroups == 0).
+  const bool device_bounds = on_device && !T;
+  float3 bmin = make_float3(0.f, 0.f, 0.f), binv = make_float3(1.f, 1.f, 1.f);
+  if (device_bounds) {
+    m.n_vgroups = 0;
   } else {
-    memcpy(hv.data(), verts, hv.size() * sizeof(float));
+    std::vector<float> hv((size_t)n_verts * 3);
+    if (on_device) {
+      NM_CHECK_CUDA(ctx, cudaMemcpyAsync(hv.data(), verts, hv.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+      NM_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    } else {
+      memcpy(hv.data(), verts, hv.size() * sizeof(float));
+    }
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int v = 0; v < n_verts; ++v)
+      for (int c = 0; c < 3; ++c) { lo[c] = fminf(lo[c], hv[3 * v + c]); hi[c] = fmaxf(hi[c], hv[3 * v + c]); }
+    if ((rc = nm_impl_build_vgroups(ctx, m, hv.data(), lo, hi, st))) return rc;      // near/far cull structure (rays.cu)
+    bmin = make_float3(lo[0], lo[1], lo[2]);
+    binv = make_float3(1.f / fmaxf(hi[0] - lo[0], 1e-20f), 1.f / fmaxf(hi[1] - lo[1], 1e-20f), 1.f / fmaxf(hi[2] - lo[2], 1e-20f));
   }
-  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  for (int v = 0; v < n_verts; ++v)
-    for (int c = 0; c < 3; ++c) { lo[c] = fminf(lo[c], hv[3 * v + c]); hi[c] = fmaxf(hi[c], hv[3 * v + c]); }
-  if ((rc = nm_impl_build_vgroups(ctx, m, hv.data(), lo, hi, st))) return rc;      // near/far cull structure (rays.cu)
-  float3 bmin = make_float3(lo[0], lo[1], lo[2]);
-  float3 binv = make_float3(1.f / fmaxf(hi[0] - lo[0], 1e-20f), 1.f / fmaxf(hi[1] - lo[1], 1e-20f), 1.f / fmaxf(hi[2] - lo[2], 1e-20f));
   size_t cub_bytes = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, n_faces);
   BvhLayout L = bvh_layout(n_faces, cub_bytes);
@@ -415,7 +449,15 @@ extern "C" int nm_mesh_set(nm_ctx* ctx, int actor, const float* verts, int32_t n
   auto* keys_in = reinterpret_cast<unsigned long long*>(base + L.keys_in);
   auto* keys_out = reinterpret_cast<unsigned long long*>(base + L.keys_out);
   float* tri9 = reinterpret_cast<float*>(base + L.tri9);
-  k_bvh_keys<<<(n_faces + 127) / 128, 128, 0, st>>>(m.verts, m.faces, n_faces, bmin, binv, tri9, keys_in);
+  int* box = nullptr;
+  if (device_bounds) {
+    box = reinterpret_cast<int*>(base + L.box);
+    NM_CHECK_CUDA(ctx, cudaMemsetAsync(box, 0x7f, 3 * sizeof(int), st));
+    NM_CHECK_CUDA(ctx, cudaMemsetAsync(box + 3, 0x80, 3 * sizeof(int), st));
+    k_bbox<<<(n_verts + 255) / 256, 256, 0, st>>>(m.verts, n_verts, box);
+    NM_CHECK_LAUNCH(ctx);
+  }
+  k_bvh_keys<<<(n_faces + 127) / 128, 128, 0, st>>>(m.verts, m.faces, n_faces, bmin, binv, box, tri9, keys_in);
   NM_CHECK_LAUNCH(ctx);
   NM_CHECK_CUDA(ctx, cub::DeviceRadixSort::SortKeys(base + L.cub_tmp, cub_bytes, keys_in, keys_out, n_faces, 0, 64, st));
   NM_LAUNCHED(ctx);
@@ -528,15 +570,15 @@ __global__ void k_edge_adjacency(const unsigned long long* __restrict__ keys, co
 
 __global__ void __launch_bounds__(128) k_signed_distance(BvhView B, const float* __restrict__ verts, const int32_t* __restrict__ faces,
                                                           const double* __restrict__ vnorm, const int32_t* __restrict__ adj,
-                                                          const float* __restrict__ pts, long long n, double* __restrict__ S_out,
+                                                          const float* __restrict__ pts, long long n,
+                                                          const int32_t* __restrict__ face_in, double* __restrict__ S_out,
                                                           int32_t* __restrict__ I_out, double* __restrict__ C_out) {
+  // face_in: the winners of k_warp_nearest (the traversal runs as its own 38-register kernel, like the warp stage; this
+  // kernel is then the float64 evaluation only)
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = i < n;
-  const long long ii = live ? i : n - 1;
-  V3<float> p{pts[3 * ii], pts[3 * ii + 1], pts[3 * ii + 2]};
-  __shared__ int s_stack[4][64];
-  const int f = bvh_nearest_face(B, p, s_stack[threadIdx.x >> 5]);
-  if (!live) return;
+  if (i >= n) return;
+  V3<float> p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+  const int f = face_in[i];
   const int iv[3] = {faces[3 * f], faces[3 * f + 1], faces[3 * f + 2]};
   const V3<double> P{(double)p.x, (double)p.y, (double)p.z};
   const V3<double> A = ld3d(verts, iv[0]), Bv = ld3d(verts, iv[1]), C = ld3d(verts, iv[2]);
@@ -609,7 +651,21 @@ extern "C" int nm_signed_distance(nm_ctx* ctx, int actor, const float* pts, int6
     int rc = build_pseudonormals(ctx, m, st);
     if (rc != NM_OK) return rc;
   }
-  k_signed_distance<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(bvh_view(m), m.verts, m.faces, m.vnorm, m.adj, pts, n, S, I, C);
+  // winning faces: the caller's buffer, or a private scratch
+  int32_t* fid = I;
+  if (!fid) {
+    if ((size_t)n > ctx->face_cap) {
+      if (ctx->face_tmp) { NM_CHECK_CUDA(ctx, cudaDeviceSynchronize()); NM_CHECK_CUDA(ctx, cudaFree(ctx->face_tmp)); ctx->face_tmp = nullptr; }
+      size_t want = (size_t)n + ((size_t)n >> 3);
+      NM_CHECK_CUDA(ctx, cudaMalloc(&ctx->face_tmp, want * sizeof(int32_t)));
+      ctx->face_cap = want;
+    }
+    fid = ctx->face_tmp;
+  }
+  const long long warps = (n + 31) / 32;
+  k_warp_nearest<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(bvh_view(m), pts, (long long)n, 1, 0, fid);
+  NM_CHECK_LAUNCH(ctx);
+  k_signed_distance<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(bvh_view(m), m.verts, m.faces, m.vnorm, m.adj, pts, n, fid, S, I, C);
   NM_CHECK_LAUNCH(ctx);
   return NM_OK;
 }

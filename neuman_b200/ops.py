@@ -320,6 +320,28 @@ def merge_samples(z_list, raw_list):
 # ---------------------------------------------------------------------------------------------
 # observation -> canonical warp
 # ---------------------------------------------------------------------------------------------
+_FACES_CACHE = {}
+
+
+def faces_device(faces, device):
+    """faces [F,>=3] (numpy / tensor) -> contiguous int32 [F,3] on `device`.  The topology is the same array step after step
+    (the SMPL faces): host arrays are uploaded once and found again by (address, shape, checksum)."""
+    device = torch.device(device)
+    if isinstance(faces, torch.Tensor):
+        if faces.device == device and faces.dtype == torch.int32 and faces.shape[1] == 3 and faces.is_contiguous():
+            return faces
+        return faces.detach()[:, :3].to(device=device, dtype=torch.int32).contiguous()
+    a = np.asarray(faces)
+    key = (a.__array_interface__['data'][0], a.shape, a.dtype.str, int(a[:, :3].sum()), str(device))
+    hit = _FACES_CACHE.get(key)
+    if hit is None:
+        if len(_FACES_CACHE) >= 8:
+            _FACES_CACHE.pop(next(iter(_FACES_CACHE)))
+        hit = torch.from_numpy(np.ascontiguousarray(a[:, :3], dtype=np.int32)).to(device)
+        _FACES_CACHE[key] = hit
+    return hit
+
+
 def set_mesh(verts, faces, T, actor=0, device=None):
     """Uploads one actor's per-frame mesh (verts [V,3], faces [F,>=3], T [>=V,4,4] or None) and builds the BVH.
     CUDA tensors are taken from device memory, anything else goes through host arrays."""
@@ -327,10 +349,7 @@ def set_mesh(verts, faces, T, actor=0, device=None):
         device = verts.device
         ctx = Context.get(device.index if device.index is not None else torch.cuda.current_device())
         v = verts.detach().float().contiguous()
-        if isinstance(faces, torch.Tensor):
-            f = faces.detach()[:, :3].to(device=device, dtype=torch.int32).contiguous()
-        else:
-            f = torch.from_numpy(np.ascontiguousarray(np.asarray(faces)[:, :3], dtype=np.int32)).to(device)
+        f = faces_device(faces, device)
         t = None
         if T is not None:
             t = (T.detach() if isinstance(T, torch.Tensor) else torch.as_tensor(np.asarray(T))).to(device=device, dtype=torch.float64)

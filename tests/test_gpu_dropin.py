@@ -278,3 +278,83 @@ def test_reference_human_trainer_step_runs_on_the_cuda_path(ref):
         ops.signed_distance = ops_sd
         igl_stub.signed_distance = stub_sd
         nb.install(ref_import.REF_ROOT)             # back to the module fixture's state (inference drop-in)
+
+
+def _reference_loss_standin(ref, device):
+    """The stand-in trainer of _reference_human_trainer_case extended with what HumanNeRFTrainer.loss_func
+    (trainers/human_nerf_trainer.py:382-446) and its regularisers (:279-380) read: penalties, the canonical-space capture
+    list, the capture's canonical mesh (verts_packed / faces_packed), interval_comp, and the trainer's own methods bound to it."""
+    import importlib
+    import types
+    tr = importlib.import_module("trainers.human_nerf_trainer")
+    me, net = _reference_human_trainer_case(ref, device)
+    for j in (net.coarse_human_net, net.coarse_bkg_net, net.fine_bkg_net):
+        scenes.boost_density(j)                       # default-init densities are <= 0 over the body: the step would re-initialise
+    opt = me.opt
+    opt.white_bkg, opt.importance_samples_per_ray, opt.samples_per_ray = True, 16, 24
+    opt.penalize_outside_factor, opt.dist_exponent = 2.0, 2.0
+    with torch.no_grad():
+        can_v = net.body_model(poses=net.da_smpl, betas=net.betas[0][None], return_tensor=True).detach().cpu()
+    faces = net.body_model.faces_tensor.cpu()
+    me.val_dataset.scene.captures[0].can_mesh = types.SimpleNamespace(verts_packed=lambda: can_v, faces_packed=lambda: faces)
+    K, c2w = scenes.camera(32, 32, seed=5, eye=(0.0, 0.0, -3.0))
+    cam = ref.pinhole_camera.PinholeCamera(32, 32, K[0, 0], K[1, 1], K[0, 2], K[1, 2])
+    me.can_caps = [ref.captures.BasePinholeCapture(cam, ref.camera_pose.CameraPose.from_camera_to_world(c2w.astype(np.float64)))]
+    me.penalize_smpl_alpha, me.penalize_symmetric_alpha, me.penalize_dummy = 0.1, 0.1, 0.0
+    me.penalize_hard_surface, me.penalize_sharp_edge = 0.1, 0.1
+    me.penalize_color_range, me.penalize_outside, me.penalize_mask, me.penalize_lpips = 0.0, 0.0, 0.01, 0.0   # (random dummy directions / LPIPS off)
+    me.interval_comp = 0.8
+    for name in ("_eval_bkg_samples", "_eval_human_samples", "_smpl_symmetry_regularization", "_color_range_regularization",
+                 "_smpl_shape_regularization", "_sparsity_regularization"):
+        setattr(me, name, types.MethodType(getattr(tr.HumanNeRFTrainer, name), me))
+    return tr, me, net
+
+
+def test_reference_human_loss_func_runs_on_the_cuda_path(ref):
+    """The reference's whole HumanNeRFTrainer.loss_func (trainers/human_nerf_trainer.py:382-446: background branch,
+    human branch, symmetry / mask / SMPL-shape / sparsity regularisers, z-sorted merge, RGB loss) with install(train=True),
+    called unmodified, against the same call of the unpatched reference on the CPU; then loss.backward()."""
+    import random
+    from neuman_b200 import dropin
+    dropin.uninstall()
+    try:
+        tr, me_c, net_c = _reference_loss_standin(ref, "cpu")
+        with torch.no_grad():
+            V0 = net_c.vertex_forward(0)[0][0].numpy()
+        rng = np.random.RandomState(3)
+        R = 64
+        eye = V0.mean(0) + np.array([0.0, 0.0, -2.0])
+        d = V0[rng.randint(0, V0.shape[0], R)] + rng.normal(0, 0.01, (R, 3)) - eye
+        dist = np.linalg.norm(d, axis=1, keepdims=True)
+        is_hit = (rng.uniform(size=R) < 0.8).astype(np.int64)
+        color = rng.uniform(size=(R, 3))
+        f = lambda a: torch.from_numpy(np.asarray(a)).float()[None]
+
+        def mk():                                    # a DataLoader batch (leading axis 1, CPU tensors), datasets/human_rays.py:233-247
+            return {"origin": f(np.repeat(eye[None], R, 0)), "direction": f(d / dist), "human_near": f(dist - 0.15),
+                    "human_far": f(dist + 0.15), "bkg_near": f(np.full((R, 1), 0.5)), "bkg_far": f(np.full((R, 1), 4.0)),
+                    "color": f(color), "is_bkg": torch.from_numpy(1 - is_hit)[None], "is_hit": torch.from_numpy(is_hit)[None],
+                    "cur_view_f": torch.tensor([3 / 11]), "cur_view": torch.tensor([3]), "cap_id": torch.tensor([0]),
+                    "patch_counter": torch.tensor([0])}
+        random.seed(0)
+        np.random.seed(0)
+        ld_c = quiet(tr.HumanNeRFTrainer.loss_func, me_c, mk())
+        nb.install(ref_import.REF_ROOT, train=True)
+        _, me_g, net_g = _reference_loss_standin(ref, "cuda")
+        net_g.load_state_dict(net_c.state_dict())
+        random.seed(0)
+        np.random.seed(0)
+        l0 = launches()
+        ld_g = quiet(tr.HumanNeRFTrainer.loss_func, me_g, mk())
+        assert launches() - l0 >= 30, "the reference's loss_func did not reach libneuman_b200"
+        assert float(ld_c["fine_rgb_loss"]) > 1e-3 and float(ld_c["smpl_shape_reg"]) > 1e-3       # a live step, not the re-init branch
+        for k, v in ld_c.items():
+            g, c = float(ld_g[k]), float(v)
+            assert abs(g - c) < 2e-2 * abs(c) + 2e-5, (k, g, c)
+        total = sum(ld_g.values())
+        total.backward()
+        for p in list(net_g.coarse_human_net.parameters()) + list(net_g.offset_nets.parameters()) + [net_g.poses, net_g.betas, net_g.alignments]:
+            assert p.grad is not None and torch.isfinite(p.grad).all()
+        assert float(net_g.poses.grad.abs().max()) > 0 and float(net_g.coarse_human_net.nerf.alpha_linear.weight.grad.abs().max()) > 0
+    finally:
+        nb.install(ref_import.REF_ROOT)
