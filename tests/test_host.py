@@ -253,6 +253,65 @@ def test_frame_metrics_against_opencv(tmp_path):
     assert abs(metrics.ssim(pred[..., :1], gt[..., :1]) - S.mean()) < 1e-9
 
 
+def test_lpips_restatement_structure_and_formula():
+    """neuman_b200.metrics.LPIPS (render_test_views.py:19,36-38; trainers/human_nerf_trainer.py:152,432-435).  The package
+    and its weights are absent (parity UNPINNED); what can be checked here: the package's parameter names, the feature
+    stack against torchvision's AlexNet with the same weights, the distance against a numpy restatement of the published
+    formula, and the two call sites' tensor conventions."""
+    torchvision = pytest.importorskip("torchvision")
+    from neuman_b200 import metrics
+    m = metrics.LPIPS()
+    keys = list(m.state_dict())
+    want = ['scaling_layer.shift', 'scaling_layer.scale']
+    for sl, idx in ((1, 0), (2, 3), (3, 6), (4, 8), (5, 10)):
+        want += [f'net.slice{sl}.{idx}.weight', f'net.slice{sl}.{idx}.bias']
+    want += [f'lin{k}.model.1.weight' for k in range(5)] + [f'lins.{k}.model.1.weight' for k in range(5)]
+    assert keys == want and not m.training and not m.pretrained
+    torch.manual_seed(0)
+    alex = torchvision.models.alexnet(weights=None).eval()
+    lin = {f'lin{k}.model.1.weight': torch.rand(1, c, 1, 1) for k, c in enumerate(metrics.LPIPS.CHNS)}
+    m.load_pretrained(alex.state_dict(), lin)
+    assert m.pretrained
+    x, y = torch.rand(2, 3, 64, 48) * 2 - 1, torch.rand(2, 3, 64, 48) * 2 - 1
+    # feature stack == torchvision's features at its five ReLUs
+    h, taps = m.scaling_layer(x), []
+    for i, layer in enumerate(alex.features[:12]):
+        h = layer(h)
+        if i in (1, 4, 7, 9, 11):
+            taps.append(h)
+    for a, b in zip(m.net(m.scaling_layer(x)), taps):
+        assert torch.equal(a, b)
+    # distance == the published formula, restated in numpy
+    with torch.no_grad():
+        got = m(x, y).numpy()
+        fx, fy = [t.numpy() for t in m.net(m.scaling_layer(x))], [t.numpy() for t in m.net(m.scaling_layer(y))]
+    val = np.zeros((2, 1, 1, 1))
+    for k in range(5):
+        ux = fx[k] / (np.sqrt((fx[k] ** 2).sum(1, keepdims=True)) + 1e-10)
+        uy = fy[k] / (np.sqrt((fy[k] ** 2).sum(1, keepdims=True)) + 1e-10)
+        w = lin[f'lin{k}.model.1.weight'].numpy()[0][None]
+        val += (((ux - uy) ** 2) * w).sum(1, keepdims=True).mean((2, 3), keepdims=True)
+    assert np.abs(got - val).max() < 1e-6
+    with torch.no_grad():
+        assert float(m(x, x).abs().max()) == 0.0
+        assert torch.allclose(m((x + 1) / 2, (y + 1) / 2, normalize=True), m(x, y), atol=1e-6)
+    # the trainer's patch term: first 1024 rays of the batch, unbatched [3,32,32] tensors (:432-435)
+    rgb, col = torch.rand(1400, 3, requires_grad=True), torch.rand(1400, 3)
+    loss = metrics.lpips_patch_loss(m, rgb, col)
+    assert loss.dim() == 0 and loss.requires_grad
+    loss.backward()
+    assert rgb.grad[:1024].abs().max() > 0 and rgb.grad[1024:].abs().max() == 0
+    # the evaluation script's call (uint8 frames -> /127.5 - 1)
+    rng = np.random.RandomState(0)
+    gt = rng.randint(0, 256, (40, 56, 3)).astype(np.uint8)
+    pred = np.clip(gt + rng.normal(0, 10, gt.shape), 0, 255).astype(np.uint8)
+    r = metrics.eval_metrics([gt], [pred], lpips_fn=m)
+    with torch.no_grad():
+        ref_val = float(m(torch.from_numpy(pred).permute(2, 0, 1)[None].float() / 127.5 - 1,
+                          torch.from_numpy(gt).permute(2, 0, 1)[None].float() / 127.5 - 1)[0, 0, 0, 0])
+    assert set(r) == {"ssim", "psnr", "lpips"} and abs(r["lpips"] - ref_val) < 1e-7 and r["lpips"] > 0
+
+
 def test_batchers_host_logic_equals_the_reference_datasets(monkeypatch):
     """The host logic of neuman_b200.data (segment plan, patch window, gathers, near/far cache lookup, dtypes) on CPU
     tensors against the batches the UNMODIFIED reference datasets produced (tests/golden/batches.npz): the ray kernel
