@@ -33,8 +33,29 @@ class Embedder(nn.Module):
         self.mapping = mapping
         self.out_dim = input_dims + 2 * input_dims * N_freqs if mapping == 'posenc' else 3 + 6 * N_freqs
 
+    def rotate_bvals(self, device=None):
+        """The 'rotate' frequency matrix [3 N, 3] (models/vanilla.py:44-58): axis-aligned frequencies rotated by 45 degrees
+        about z, then by 45 degrees about x; built in float64 and rounded to float32 like the reference."""
+        b = 2.0 ** np.linspace(self.min_freq, self.max_freq, num=self.N_freqs)
+        b = np.reshape(np.eye(3) * b[:, None, None], [len(b) * 3, 3])
+        h = (2 ** .5) / 2
+        b = b @ np.array([[h, -h, 0], [h, h, 0], [0, 0, 1]]).T
+        b = b @ np.array([[1, 0, 0], [0, h, -h], [0, h, h]]).T
+        return torch.from_numpy(b).float().to(device)
+
     def forward(self, inputs, cur_iter=None):
-        raise NotImplementedError("Embedder is fused into the MLP kernel; call Joiner.forward")
+        """models/vanilla.py:82-92 as stand-alone torch ops (any device).  The renderers and trainers never call it: inside
+        `Joiner.forward` / `OffsetNet.forward` the encoding is produced by the MLP kernels' own encoding warps (csrc/nm_pe.cuh).
+        It exists so that code written against the reference's module interface keeps working."""
+        if self.mapping == 'rotate':
+            assert inputs.shape[-1] == 3
+            proj = inputs @ self.rotate_bvals(inputs.device).T
+            return torch.cat([inputs, torch.sin(proj), torch.cos(proj)], -1)
+        assert cur_iter is None
+        out = [inputs]
+        for f in 2.0 ** torch.linspace(self.min_freq, self.max_freq, steps=self.N_freqs):
+            out += [torch.sin(inputs * f), torch.cos(inputs * f)]
+        return torch.cat(out, -1)
 
 
 class NeRF(nn.Module):
@@ -65,7 +86,32 @@ class NeRF(nn.Module):
         self.rgb_linear = nn.Linear(width // 2, 3)
 
     def forward(self, input_pts, input_views=None):
-        raise NotImplementedError("NeRF consumes encoded inputs; the fused CUDA path is Joiner.forward")
+        """models/vanilla.py:120-152 on ALREADY ENCODED inputs, as library GEMMs (torch.nn.functional.linear; any device).
+        The product path never takes it -- `Joiner.forward` runs encoding + network as one tensor-core kernel -- it serves code
+        that drives the reference's module interface layer by layer."""
+        import torch.nn.functional as F
+        assert input_pts.shape[-1] == self.input_ch
+        h = input_pts
+        for i, lin in enumerate(self.pts_linears):
+            h = F.relu(lin(h))
+            if i in self.skips:
+                h = torch.cat([input_pts, h], -1)
+        if self.use_viewdirs:
+            assert input_views is not None and input_views.shape[-1] == self.input_ch_views
+            alpha = self.alpha_linear(h)
+            h = torch.cat([self.feature_linear(h), input_views], -1)
+            for lin in self.views_linears:
+                h = F.relu(lin(h))
+            out = torch.cat([self.rgb_linear(h), alpha], -1)
+        else:
+            out = self.output_linear(h)
+        if self.scale_type == 'no':
+            return out
+        if self.scale_type == 'linear':
+            return out * self.scale
+        if self.scale_type == 'tanh':
+            return torch.tanh(out) * self.scale
+        raise ValueError(self.scale_type)
 
 
 class Joiner(nn.Module):

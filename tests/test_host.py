@@ -70,6 +70,27 @@ def test_offset_net_equals_reference(scale_type):
         assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-7), k
 
 
+@pytest.mark.reference
+@pytest.mark.parametrize("posenc", ["posenc", "rotate"])
+def test_module_interface_layer_by_layer_equals_reference(posenc):
+    """SURVEY.md 8b lists Embedder.forward and NeRF.forward among the signatures to preserve: the mirrors evaluate them with
+    library ops (the fused kernels serve Joiner.forward); bit-equal to the reference's modules on the CPU, and
+    NeRF(Embedder(x), Embedder(v)) == the reference's Joiner."""
+    from oracle import ref_import, ref_opts
+    ref = ref_import.load()
+    torch.manual_seed(2)
+    mine, _ = nb.build_nerf(nb.default_opt(use_cuda=False, posenc=posenc))
+    torch.manual_seed(2)
+    theirs, _ = ref.vanilla.build_nerf(ref_opts.default_opt(posenc=posenc))
+    for pe in (theirs.pos_pe, theirs.dir_pe):
+        if hasattr(pe, "bvals"):
+            pe.bvals = pe.bvals.cpu()                # the reference parks them on the GPU whenever one is visible
+    x, v = torch.randn(7, 5, 3), torch.randn(7, 5, 3)
+    e, d = mine.pos_pe(x), mine.dir_pe(v)
+    assert torch.equal(e, theirs.pos_pe(x)) and torch.equal(d, theirs.dir_pe(v)) and e.shape[-1] == 63 and d.shape[-1] == 27
+    assert torch.equal(mine.nerf(e, d), theirs(x, v))
+
+
 def test_shard_ranges_cover_every_pixel_once():
     for n, world in ((921600, 8), (4096, 3), (10, 4), (7, 8), (0, 2)):
         seen = np.zeros(n, dtype=np.int32)
