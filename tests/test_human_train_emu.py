@@ -263,3 +263,33 @@ def test_autograd_bindings_on_the_emulated_library(monkeypatch):
     ((T_o * g1).sum() + (world_o * g2).sum()).backward()
     for got, want in ((pose.grad, po.grad), (betas.grad, bo.grad), (al.grad, ao.grad)):
         assert got.shape == want.shape and (got - want).abs().max() < 5e-4 * (1 + want.abs().max())
+
+
+@pytest.mark.parametrize("R,S", [(1, 2), (3, 2), (5, 7), (1, 33)])
+def test_warp_diff_kernels_edge_shapes(R, S):
+    """Smallest legal ray (two samples: the second direction is the copy of the first), single rays, sizes that do not fill
+    a block; optional outputs left out (null pointers)."""
+    L = emu.lib()
+    V, F, T, P, I, Cl, off = _case(seed=11, R=R, S=S)
+    n = R * S
+    cp, cd = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+    L.emu_wd_forward(ptr(I), ptr(f64(Cl)), ptr(V), ptr(F), ptr(T), ptr(f32(P)), None, C.c_longlong(n), None, ptr(cp))
+    L.emu_wd_dirs(ptr(cp), C.c_longlong(R), C.c_int(S), ptr(cd))
+    Vt, Tt = torch.from_numpy(V).requires_grad_(True), torch.from_numpy(T).reshape(-1, 4, 4).requires_grad_(True)
+    cp_o, cd_o = no.eval_human_samples(torch.from_numpy(P), Cl, I, Vt, F, Tt, None)
+    assert np.abs(cp.reshape(R, S, 3) - cp_o.detach().numpy()).max() < 2e-6
+    assert np.abs(cd.reshape(R, S, 3) - cd_o.detach().numpy()).max() < 5e-5
+    assert np.abs(cd.reshape(R, S, 3)[:, -1] - cd.reshape(R, S, 3)[:, -2]).max() == 0          # last direction = the previous one
+    rng = np.random.RandomState(R * 100 + S)
+    g_cd = rng.normal(0, 1, (R, S, 3)).astype(np.float32)
+    (cd_o * torch.from_numpy(g_cd)).sum().backward()
+    g_tot = np.zeros((n, 3), np.float32)
+    L.emu_wd_dirs_backward(ptr(cp), None, ptr(g_cd), C.c_longlong(R), C.c_int(S), ptr(g_tot))
+    gT = np.zeros_like(T)
+    L.emu_wd_backward(ptr(I), ptr(f64(Cl)), ptr(V), ptr(F), ptr(T), ptr(f32(P)), None, ptr(g_tot), C.c_longlong(n), ptr(gT), None)   # no vertex gradient wanted
+    wT = Tt.grad.numpy().reshape(-1, 16)
+    assert np.abs(gT - wT).max() < 5e-4 * (1 + np.abs(wT).max())
+    gV = np.zeros_like(V)
+    L.emu_wd_backward(ptr(I), ptr(f64(Cl)), ptr(V), ptr(F), ptr(T), ptr(f32(P)), None, ptr(g_tot), C.c_longlong(n), None, ptr(gV))   # only the vertex gradient
+    wV = Vt.grad.numpy()
+    assert np.abs(gV - wV).max() < 5e-4 * (1 + np.abs(wV).max())
