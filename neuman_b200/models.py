@@ -248,18 +248,44 @@ def offset_channel_split(n_freqs):
     return xyz, tt
 
 
+def _offset_consts(net, dev):
+    """Per-device constants of the Joiner form (index lists, frequencies, the fixed head weights): built once and kept
+    on the instance, so that a training step issues no host->device copy for them."""
+    pe = net.pos_pe
+    key = (str(dev), int(pe.N_freqs), float(pe.min_freq), float(pe.max_freq))
+    cache = net.__dict__.setdefault('_nm_consts', {})
+    c = cache.get(key)
+    if c is None:
+        with torch.inference_mode(False), torch.no_grad():
+            xyz, tt = offset_channel_split(pe.N_freqs)
+            vw = torch.zeros(128, 256 + 27)
+            vw[torch.arange(6), torch.arange(6)] = 1.0
+            rw = torch.zeros(3, 128)
+            rw[torch.arange(3), torch.arange(3)] = 1.0
+            rw[torch.arange(3), torch.arange(3) + 3] = -1.0
+            c = {'xyz': torch.tensor(xyz).to(dev), 'tt': torch.tensor(tt).to(dev),
+                 'freqs': (2.0 ** torch.linspace(pe.min_freq, pe.max_freq, steps=pe.N_freqs)).to(dev),
+                 'pad_w': torch.zeros(250, 256).to(dev), 'pad_b': torch.zeros(250).to(dev),
+                 'alpha_w': torch.zeros(1, 256).to(dev), 'alpha_b': torch.zeros(1).to(dev),
+                 'views_w': vw.to(dev), 'views_b': torch.zeros(128).to(dev), 'rgb_w': rw.to(dev), 'rgb_b': torch.zeros(3).to(dev)}
+        cache.clear()                                          # one device at a time is all a module lives on
+        cache[key] = c
+    return c
+
+
 def offset_joiner_weights(net, t):
     """The Joiner-shaped parameters equivalent to offset network `net` at time t (0-d tensor or float), as differentiable
     functions of its parameters; keys = NeRF(use_viewdirs=True).named_parameters() names."""
     n = net.nerf
     dev = n.output_linear.weight.device
-    xyz, tt = offset_channel_split(net.pos_pe.N_freqs)
-    xyz_i, tt_i = torch.tensor(xyz, device=dev), torch.tensor(tt, device=dev)
-    t = torch.as_tensor(t, dtype=torch.float32, device=dev).reshape(())
-    pe_t = [t[None]]
-    for f in _offset_freqs(net, dev):
-        pe_t += [torch.sin(t * f)[None], torch.cos(t * f)[None]]
-    pe_t = torch.cat(pe_t)                                           # [21]
+    c = _offset_consts(net, dev)
+    xyz_i, tt_i = c['xyz'], c['tt']
+    if isinstance(t, torch.Tensor):
+        t = t.detach().to(device=dev, dtype=torch.float32).reshape(())
+    else:
+        t = torch.full((), float(t), dtype=torch.float32, device=dev)          # a fill kernel: no host->device copy
+    ft = t * c['freqs']
+    pe_t = torch.cat([t[None], torch.stack([torch.sin(ft), torch.cos(ft)], 1).reshape(-1)])      # [t, sin f0 t, cos f0 t, sin f1 t, ...]
     n_in = net.pos_pe.out_dim                                        # 84
     W = {}
     for l, lin in enumerate(n.pts_linears):
@@ -273,17 +299,11 @@ def offset_joiner_weights(net, t):
         else:
             W[f'pts_linears.{l}.weight'], W[f'pts_linears.{l}.bias'] = w, b
     wo, bo = n.output_linear.weight, n.output_linear.bias
-    z = lambda *s: torch.zeros(*s, device=dev)
-    W['feature_linear.weight'] = torch.cat([wo, -wo, z(250, 256)], 0)
-    W['feature_linear.bias'] = torch.cat([bo, -bo, z(250)])
-    W['alpha_linear.weight'], W['alpha_linear.bias'] = z(1, 256), z(1)
-    vw = z(128, 256 + 27)
-    vw[torch.arange(6), torch.arange(6)] = 1.0
-    W['views_linears.0.weight'], W['views_linears.0.bias'] = vw, z(128)
-    rw = z(3, 128)
-    rw[torch.arange(3), torch.arange(3)] = 1.0
-    rw[torch.arange(3), torch.arange(3) + 3] = -1.0
-    W['rgb_linear.weight'], W['rgb_linear.bias'] = rw, z(3)
+    W['feature_linear.weight'] = torch.cat([wo, -wo, c['pad_w']], 0)
+    W['feature_linear.bias'] = torch.cat([bo, -bo, c['pad_b']])
+    W['alpha_linear.weight'], W['alpha_linear.bias'] = c['alpha_w'], c['alpha_b']
+    W['views_linears.0.weight'], W['views_linears.0.bias'] = c['views_w'], c['views_b']
+    W['rgb_linear.weight'], W['rgb_linear.bias'] = c['rgb_w'], c['rgb_b']
     return W
 
 

@@ -91,6 +91,34 @@ def test_module_interface_layer_by_layer_equals_reference(posenc):
     assert torch.equal(mine.nerf(e, d), theirs(x, v))
 
 
+def test_offset_net_joiner_form_stays_on_the_modules_device():
+    """Device placement of models.offset_joiner_weights without a GPU: on the `meta` device every intermediate must be
+    created on the module's device (mixing in a CPU tensor raises there exactly as it would with CUDA); the architecture
+    constants are built once per device and reused; a tensor time works like a float."""
+    from neuman_b200 import models
+    net = nb.build_offset_net(nb.default_opt(use_cuda=False, num_offset_nets=1, offset_scale_type='tanh'))
+    meta = copy_to(net, 'meta')
+    for t in (0.3, torch.tensor(0.3, device='meta')):
+        W = models.offset_joiner_weights(meta, t)
+        assert all(v.device.type == 'meta' for v in W.values())
+    j = models.offset_shadow_joiner(meta)
+    assert all(p.device.type == 'meta' and not p.requires_grad for p in j.parameters())
+    W1, W2 = models.offset_joiner_weights(net, 0.25), models.offset_joiner_weights(net, torch.tensor(0.25))
+    assert all(torch.equal(W1[k], W2[k]) for k in W1)
+    assert W1['views_linears.0.weight'] is W2['views_linears.0.weight'] and W1['rgb_linear.weight'] is W2['rgb_linear.weight']
+    assert not W1['rgb_linear.weight'].requires_grad and W1['feature_linear.weight'].requires_grad
+    fresh = nb.build_offset_net(nb.default_opt(use_cuda=False, num_offset_nets=1))
+    with torch.inference_mode():                      # constants first built inside inference mode must stay usable by autograd
+        models.offset_joiner_weights(fresh, 0.1)
+    Wf = models.offset_joiner_weights(fresh, 0.1)
+    torch.autograd.grad(sum((v * v).sum() for v in Wf.values() if v.requires_grad), list(fresh.nerf.parameters()))
+
+
+def copy_to(module, device):
+    import copy
+    return copy.deepcopy(module).to(device)
+
+
 def test_shard_ranges_cover_every_pixel_once():
     for n, world in ((921600, 8), (4096, 3), (10, 4), (7, 8), (0, 2)):
         seen = np.zeros(n, dtype=np.int32)
