@@ -80,13 +80,19 @@ def test_warp_diff_forward_and_backward_kernels():
     assert np.abs((only + g_cp.reshape(-1, 3)) - g_tot).max() < 1e-5
 
 
-def test_smpl_scene_forward_and_backward_kernels():
-    """HumanNeRF.vertex_forward (models/human_nerf.py:92-122) and its adjoint to poses / betas / alignments."""
+@pytest.mark.parametrize("zero_joints", [False, True])
+def test_smpl_scene_forward_and_backward_kernels(zero_joints):
+    """HumanNeRF.vertex_forward (models/human_nerf.py:92-122) and its adjoint to poses / betas / alignments; also with joints
+    whose axis-angle is exactly zero (the Rodrigues formula of models/smpl.py:422 divides by |r + 1e-8|)."""
     L = emu.lib()
     model = synth_smpl.torch_model(0)
     nv, nj, nb = model["v_template"].shape[0], model["parents"].shape[0], model["shapedirs"].shape[-1]
     rng = np.random.RandomState(4)
-    pose = torch.from_numpy(rng.normal(0, 0.3, (1, 3 * nj))).float().requires_grad_(True)
+    p0 = rng.normal(0, 0.3, (1, 3 * nj))
+    if zero_joints:
+        p0[0, 0:3] = 0.0
+        p0[0, 15:27] = 0.0
+    pose = torch.from_numpy(p0).float().requires_grad_(True)
     betas = torch.from_numpy(rng.normal(0, 1.0, (1, nb))).float().requires_grad_(True)
     ang = 0.2
     align = np.eye(4, dtype=np.float32)
